@@ -1,0 +1,106 @@
+// Curve traits: compile-time parameters + constant-memory tables for BN254, BLS12-381, BLS12-377
+// (the three curves of BASELINE.json; mathlib CurveIDs 1, 3/5/6/7, 4 -- reference math.go:70-103).
+#pragma once
+#include "fp.cuh"
+#include "constants.h"
+
+namespace b200 {
+
+template <int N>
+struct CurveConsts {
+    uint32_t p[N];
+    uint32_t one[N];
+    uint32_t r2[N];
+    uint32_t b[N];          // G1 curve coefficient b (Montgomery)
+    uint32_t b3[N];         // 3b
+    uint32_t btw[2 * N];    // twist coefficient b' in Fp2 (Montgomery)
+    uint32_t order[8];      // group order r, little-endian words
+    uint32_t frob1[10 * N]; // gamma_{1,i} = xi^(i(p-1)/6),   i=1..5, Fp2 each
+    uint32_t frob2[10 * N]; // gamma_{2,i} = xi^(i(p^2-1)/6)
+    uint32_t frob3[10 * N]; // gamma_{3,i} = xi^(i(p^3-1)/6)
+};
+
+#define B200_DEFINE_CONSTS(NAME, NL)                                                        \
+    static const CurveConsts<NL> H_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2, NAME##_B,     \
+                                             NAME##_B3, NAME##_BTW, NAME##_ORDER,           \
+                                             NAME##_FROB1, NAME##_FROB2, NAME##_FROB3};
+
+B200_DEFINE_CONSTS(BN254, 8)
+B200_DEFINE_CONSTS(BLS381, 12)
+B200_DEFINE_CONSTS(BLS377, 12)
+
+#if defined(__CUDACC__)
+#define B200_DEFINE_DCONSTS(NAME, NL)                                                       \
+    __device__ __constant__ CurveConsts<NL> D_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2,    \
+                                                        NAME##_B, NAME##_B3, NAME##_BTW,    \
+                                                        NAME##_ORDER, NAME##_FROB1,         \
+                                                        NAME##_FROB2, NAME##_FROB3};
+B200_DEFINE_DCONSTS(BN254, 8)
+B200_DEFINE_DCONSTS(BLS381, 12)
+B200_DEFINE_DCONSTS(BLS377, 12)
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define B200_K(NAME) D_##NAME
+#else
+#define B200_K(NAME) H_##NAME
+#endif
+
+enum TwistType { TWIST_D = 0, TWIST_M = 1 };
+enum Family { FAMILY_BN = 0, FAMILY_BLS12 = 1 };
+
+struct BN254 {
+    static constexpr int N = 8;
+    static constexpr int FP_BYTES = 32;
+    static constexpr int BETA = -1;                   // u^2
+    static constexpr int XI0 = 9, XI1 = 1;            // xi = 9 + u
+    static constexpr TwistType TWIST = TWIST_D;
+    static constexpr Family FAMILY = FAMILY_BN;
+    static constexpr uint64_t X_ABS = 4965661367192848881ull;
+    static constexpr bool X_NEG = false;
+    static constexpr int FLAG_BITS = 2;
+    static constexpr int SCALAR_BITS = 254;
+    static B200_HD const CurveConsts<8>& K() { return B200_K(BN254); }
+    static B200_HD const uint32_t* p() { return K().p; }
+    static B200_HD const uint32_t* one() { return K().one; }
+    static B200_HD const uint32_t* r2() { return K().r2; }
+    static B200_HD uint32_t inv32() { return BN254_INV32; }
+};
+
+struct BLS381 {
+    static constexpr int N = 12;
+    static constexpr int FP_BYTES = 48;
+    static constexpr int BETA = -1;
+    static constexpr int XI0 = 1, XI1 = 1;            // xi = 1 + u
+    static constexpr TwistType TWIST = TWIST_M;
+    static constexpr Family FAMILY = FAMILY_BLS12;
+    static constexpr uint64_t X_ABS = 0xd201000000010000ull;
+    static constexpr bool X_NEG = true;
+    static constexpr int FLAG_BITS = 3;
+    static constexpr int SCALAR_BITS = 255;
+    static B200_HD const CurveConsts<12>& K() { return B200_K(BLS381); }
+    static B200_HD const uint32_t* p() { return K().p; }
+    static B200_HD const uint32_t* one() { return K().one; }
+    static B200_HD const uint32_t* r2() { return K().r2; }
+    static B200_HD uint32_t inv32() { return BLS381_INV32; }
+};
+
+struct BLS377 {
+    static constexpr int N = 12;
+    static constexpr int FP_BYTES = 48;
+    static constexpr int BETA = -5;
+    static constexpr int XI0 = 0, XI1 = 1;            // xi = u
+    static constexpr TwistType TWIST = TWIST_D;
+    static constexpr Family FAMILY = FAMILY_BLS12;
+    static constexpr uint64_t X_ABS = 0x8508c00000000001ull;
+    static constexpr bool X_NEG = false;
+    static constexpr int FLAG_BITS = 3;
+    static constexpr int SCALAR_BITS = 253;
+    static B200_HD const CurveConsts<12>& K() { return B200_K(BLS377); }
+    static B200_HD const uint32_t* p() { return K().p; }
+    static B200_HD const uint32_t* one() { return K().one; }
+    static B200_HD const uint32_t* r2() { return K().r2; }
+    static B200_HD uint32_t inv32() { return BLS377_INV32; }
+};
+
+}  // namespace b200

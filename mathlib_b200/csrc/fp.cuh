@@ -1,0 +1,298 @@
+// Montgomery Fp arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces the Fp layer under gnark-crypto / kilic that mathlib's adapters call (reference
+// driver/gurvy/bn254.go:248-267, driver/kilic/bls12-381.go:260-277); the one Fp multiply that
+// lives inside the reference, driver/kilic/custom_generic.go:57-175 (6x64 CIOS), computes the
+// same function a*b*R^-1 mod p with R = 2^384 -- in-memory limbs are bit-identical
+// (12 x u32 little-endian == 6 x u64 little-endian).
+//
+// Design: one field element per thread, N = 8 (BN254) or 12 (BLS12-381/377) limbs in
+// registers.  Multiplication is operand-scanning Montgomery with the partial products split
+// into an even-aligned and an odd-aligned accumulator so that every 32x32->64 product is a
+// mad.lo.cc/madc.hi.cc pair (one IMAD.WIDE.U32 in SASS) on one of two independent carry
+// chains -- the chains interleave in the FMA pipe instead of serialising on the carry flag.
+//
+// The same source compiles for the host (tests/hostemu): the PTX carry-chain primitives
+// have a C emulation below, used ONLY by the CPU-side test harness to check kernel logic
+// without a GPU.  No product entry point reaches the host path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define B200_HD inline
+#define B200_HD_NOINLINE
+#endif
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define B200_ASM_R3(name, ptx)                                                              \
+    static __device__ __forceinline__ uint32_t name(uint32_t a, uint32_t b) {               \
+        uint32_t r;                                                                         \
+        asm volatile(ptx " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                        \
+        return r;                                                                           \
+    }
+#define B200_ASM_R4(name, ptx)                                                              \
+    static __device__ __forceinline__ uint32_t name(uint32_t a, uint32_t b, uint32_t c) {   \
+        uint32_t r;                                                                         \
+        asm volatile(ptx " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));            \
+        return r;                                                                           \
+    }
+B200_ASM_R3(add_cc, "add.cc.u32")
+B200_ASM_R3(addc_cc, "addc.cc.u32")
+B200_ASM_R3(addc, "addc.u32")
+B200_ASM_R3(sub_cc, "sub.cc.u32")
+B200_ASM_R3(subc_cc, "subc.cc.u32")
+B200_ASM_R3(subc, "subc.u32")
+B200_ASM_R4(mad_lo_cc, "mad.lo.cc.u32")
+B200_ASM_R4(madc_lo_cc, "madc.lo.cc.u32")
+B200_ASM_R4(mad_hi_cc, "mad.hi.cc.u32")
+B200_ASM_R4(madc_hi_cc, "madc.hi.cc.u32")
+B200_ASM_R4(madc_hi, "madc.hi.u32")
+B200_ASM_R4(madc_lo, "madc.lo.u32")
+static __device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+static __device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+// Host emulation of the PTX condition-code register (test harness only).
+static thread_local uint32_t g_cc = 0;
+static inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + g_cc; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + g_cc; }
+static inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; g_cc = (uint32_t)((t >> 32) & 1); return (uint32_t)t; }
+static inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - g_cc; g_cc = (uint32_t)((t >> 32) & 1); return (uint32_t)t; }
+static inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_cc; }
+static inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c + g_cc; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + g_cc; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c + g_cc; }
+static inline uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((uint64_t)a * b) + c + g_cc; }
+static inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+static inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#endif
+
+// ---------------------------------------------------------------------------------------
+// field element
+// ---------------------------------------------------------------------------------------
+template <int N>
+struct alignas(16) Fp {
+    uint32_t l[N];
+};
+
+// C: curve traits (curves.cuh) -- C::N, C::p() (modulus limbs), C::inv32(), C::one()
+template <class C>
+struct FpOps {
+    static constexpr int N = C::N;
+    typedef Fp<N> E;
+
+    static B200_HD void zero(E& r) {
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+    }
+    static B200_HD void one(E& r) {
+        const uint32_t* o = C::one();
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = o[i];
+    }
+    static B200_HD bool is_zero(const E& a) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= a.l[i];
+        return t == 0;
+    }
+    static B200_HD bool eq(const E& a, const E& b) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= a.l[i] ^ b.l[i];
+        return t == 0;
+    }
+    // r = c ? a : r
+    static B200_HD void cmov(E& r, const E& a, bool c) {
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = c ? a.l[i] : r.l[i];
+    }
+
+    // conditional final subtraction: r in [0, 2p) -> [0, p)
+    static B200_HD void reduce_once(E& r) {
+        const uint32_t* p = C::p();
+        uint32_t t[N];
+        t[0] = sub_cc(r.l[0], p[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(r.l[i], p[i]);
+        uint32_t borrow = subc(0, 0);  // 0 or 0xffffffff
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = borrow ? r.l[i] : t[i];
+    }
+
+    static B200_HD void add(E& r, const E& a, const E& b) {
+        r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+        // p has >= 2 spare bits in the top limb: no carry out of N limbs
+        reduce_once(r);
+    }
+    static B200_HD void dbl(E& r, const E& a) { add(r, a, a); }
+
+    static B200_HD void sub(E& r, const E& a, const E& b) {
+        const uint32_t* p = C::p();
+        r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = subc(0, 0);
+        // add p back masked
+        r.l[0] = add_cc(r.l[0], p[0] & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], p[i] & borrow);
+        r.l[N - 1] = addc(r.l[N - 1], p[N - 1] & borrow);
+    }
+    static B200_HD void neg(E& r, const E& a) {
+        const uint32_t* p = C::p();
+        bool z = is_zero(a);
+        E t;
+        t.l[0] = sub_cc(p[0], a.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) t.l[i] = subc_cc(p[i], a.l[i]);
+        t.l[N - 1] = subc(p[N - 1], a.l[N - 1]);
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = z ? 0u : t.l[i];
+    }
+    // r = a/2 mod p
+    static B200_HD void halve(E& r, const E& a) {
+        const uint32_t* p = C::p();
+        uint32_t m = 0u - (a.l[0] & 1u);
+        uint32_t t[N];
+        t[0] = add_cc(a.l[0], p[0] & m);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = addc_cc(a.l[i], p[i] & m);
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+        r.l[N - 1] = t[N - 1] >> 1;
+    }
+
+    // ----------------------------------------------------------------------------------
+    // Montgomery multiplication r = a*b/R mod p, fully reduced.
+    // Even/odd split accumulators; see file header.  X = even-aligned words 0..N (X[N] is
+    // the carry word), Y = odd-aligned words 1..N held in Y[0..N-1].
+    // ----------------------------------------------------------------------------------
+    // acc[0..N) += v_even * m   (v[0], v[2], ...), returns with CC = carry out of word N-1
+    static B200_HD void chain_even(uint32_t* acc, const uint32_t* v, uint32_t m) {
+        acc[0] = mad_lo_cc(v[0], m, acc[0]);
+        acc[1] = madc_hi_cc(v[0], m, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            acc[j] = madc_lo_cc(v[j], m, acc[j]);
+            acc[j + 1] = madc_hi_cc(v[j], m, acc[j + 1]);
+        }
+    }
+    // acc[0..N) (odd aligned) += v_odd * m   (v[1], v[3], ...); top limb of v is < 2^30 so no carry out
+    static B200_HD void chain_odd(uint32_t* acc, const uint32_t* v, uint32_t m) {
+        acc[0] = mad_lo_cc(v[1], m, acc[0]);
+        acc[1] = madc_hi_cc(v[1], m, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2) {
+            acc[j] = madc_lo_cc(v[j + 1], m, acc[j]);
+            acc[j + 1] = madc_hi_cc(v[j + 1], m, acc[j + 1]);
+        }
+        acc[N - 2] = madc_lo_cc(v[N - 1], m, acc[N - 2]);
+        acc[N - 1] = madc_hi(v[N - 1], m, acc[N - 1]);
+    }
+
+    // One row: A = previous even-aligned accumulator (A[0]==0, stray A[1], carry word A[N]),
+    // B = previous odd-aligned accumulator.  After the 32-bit shift B is the even-aligned one
+    // and A (shifted down by two words) the odd-aligned one.
+    static B200_HD void row(uint32_t* A, uint32_t* B, const uint32_t* a, uint32_t bi) {
+        const uint32_t* p = C::p();
+        // stray word of A lands on word 0 of the new even accumulator; its carry feeds word 1
+        B[0] = add_cc(B[0], A[1]);
+        // A'[j] = A[j+2] + a_odd*bi   (shift fused into the multiply-accumulate)
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) {
+            A[j] = madc_lo_cc(a[j + 1], bi, A[j + 2]);
+            A[j + 1] = madc_hi_cc(a[j + 1], bi, A[j + 3]);
+        }
+        A[N - 2] = madc_lo_cc(a[N - 1], bi, A[N]);
+        A[N - 1] = madc_hi(a[N - 1], bi, 0);
+        // B += a_even*bi
+        chain_even(B, a, bi);
+        B[N] = addc(0, 0);
+        uint32_t m = mul_lo(B[0], C::inv32());
+        chain_odd(A, p, m);
+        chain_even(B, p, m);
+        B[N] = addc(B[N], 0);
+    }
+
+    static B200_HD void mul(E& r, const E& a, const E& b) {
+        const uint32_t* p = C::p();
+        uint32_t X[N + 2], Y[N + 2];
+        // row 0
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            X[j] = mul_lo(a.l[j], b.l[0]);
+            X[j + 1] = mul_hi(a.l[j], b.l[0]);
+            Y[j] = mul_lo(a.l[j + 1], b.l[0]);
+            Y[j + 1] = mul_hi(a.l[j + 1], b.l[0]);
+        }
+        X[N] = 0; X[N + 1] = 0; Y[N] = 0; Y[N + 1] = 0;
+        {
+            uint32_t m = mul_lo(X[0], C::inv32());
+            chain_odd(Y, p, m);
+            chain_even(X, p, m);
+            X[N] = addc(0, 0);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            row(X, Y, a.l, b.l[i]);
+            if (i + 1 < N) row(Y, X, a.l, b.l[i + 1]);
+        }
+        // N rows done; N even => last row was row(X, Y): even accumulator is Y, odd is X
+        // result = (Y >> 32) + X
+        r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(X[i], Y[i + 1]);
+        r.l[N - 1] = addc(X[N - 1], Y[N]);
+        reduce_once(r);
+    }
+    static B200_HD void sqr(E& r, const E& a) { mul(r, a, a); }
+
+    // Montgomery form conversions
+    static B200_HD void to_mont(E& r, const E& a) {
+        E r2;
+        const uint32_t* q = C::r2();
+#pragma unroll
+        for (int i = 0; i < N; i++) r2.l[i] = q[i];
+        mul(r, a, r2);
+    }
+    static B200_HD void from_mont(E& r, const E& a) {
+        E o;
+        zero(o);
+        o.l[0] = 1;
+        mul(r, a, o);
+    }
+
+    // r = a^(p-2) (Fermat).  Not constant time; inputs are public here.
+    static B200_HD_NOINLINE void inv(E& r, const E& a) {
+        const uint32_t* p = C::p();
+        E acc, base = a;
+        one(acc);
+        // exponent p-2, LSB first
+        uint32_t borrow2 = 2;
+        for (int i = 0; i < N; i++) {
+            uint32_t w = p[i];
+            uint32_t e = w - borrow2;
+            borrow2 = (w < borrow2) ? 1 : 0;
+            for (int bit = 0; bit < 32; bit++) {
+                if ((e >> bit) & 1) mul(acc, acc, base);
+                sqr(base, base);
+            }
+        }
+        r = acc;
+    }
+};
+
+}  // namespace b200

@@ -1,0 +1,67 @@
+// Host-emulation harness (TEST INFRASTRUCTURE): compiles the device headers for the CPU with the
+// PTX carry-chain primitives emulated in C, so kernel logic can be checked without a GPU.
+#include <string.h>
+#include "../../mathlib_b200/csrc/curves.cuh"
+using namespace b200;
+template <class C> static void t_mul(const uint32_t* a, const uint32_t* b, uint32_t* o, int op) {
+    typedef FpOps<C> F; typename F::E x, y, z;
+    for (int i = 0; i < C::N; i++) { x.l[i] = a[i]; y.l[i] = b[i]; }
+    switch (op) {
+        case 0: F::mul(z, x, y); break;
+        case 1: F::add(z, x, y); break;
+        case 2: F::sub(z, x, y); break;
+        case 3: F::neg(z, x); break;
+        case 4: F::halve(z, x); break;
+        case 5: F::inv(z, x); break;
+        case 6: F::to_mont(z, x); break;
+        case 7: F::from_mont(z, x); break;
+    }
+    for (int i = 0; i < C::N; i++) o[i] = z.l[i];
+}
+extern "C" void he_fp_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    if (curve == 0) t_mul<BN254>(a, b, o, op);
+    else if (curve == 1) t_mul<BLS381>(a, b, o, op);
+    else t_mul<BLS377>(a, b, o, op);
+}
+
+#include "../../mathlib_b200/csrc/pairing.cuh"
+// layout of inputs: Montgomery limbs, G1 = x|y (2N words), G2 = x.c0|x.c1|y.c0|y.c1 (4N words),
+// Gt = C0.B0.A0, C0.B0.A1, C0.B1.A0, ... C1.B2.A1 (12N words, struct order)
+template <class C> static void t_pair(int np, const uint32_t* g1, const uint32_t* g2, uint32_t* out, int mode) {
+    typedef PairingOps<C> PO;
+    constexpr int N = C::N;
+    G1Aff<N> P[2]; G2Aff<N> Q[2];
+    memcpy(P, g1, sizeof(G1Aff<N>) * np);
+    memcpy(Q, g2, sizeof(G2Aff<N>) * np);
+    Fp12<N> f;
+    if (np == 1) PO::template miller_loop<1>(f, P, Q); else PO::template miller_loop<2>(f, P, Q);
+    if (mode) PO::final_exp(f, f);
+    memcpy(out, &f, sizeof(f));
+}
+extern "C" void he_pairing(int curve, int np, const uint32_t* g1, const uint32_t* g2, uint32_t* out, int mode) {
+    if (curve == 0) t_pair<BN254>(np, g1, g2, out, mode);
+    else if (curve == 1) t_pair<BLS381>(np, g1, g2, out, mode);
+    else t_pair<BLS377>(np, g1, g2, out, mode);
+}
+template <class C> static void t_f12(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    typedef Tower<C> T; typedef PairingOps<C> PO;
+    Fp12<C::N> x, y, z;
+    memcpy(&x, a, sizeof(x)); memcpy(&y, b, sizeof(y));
+    switch (op) {
+        case 0: T::f12_mul(z, x, y); break;
+        case 1: T::f12_sqr(z, x); break;
+        case 2: T::f12_inv(z, x); break;
+        case 3: T::f12_frob(z, x, 1); break;
+        case 4: T::f12_frob(z, x, 2); break;
+        case 5: T::f12_frob(z, x, 3); break;
+        case 6: T::f12_cyclo_sqr(z, x); break;
+        case 7: PO::final_exp(z, x); break;
+        case 8: T::f12_conj(z, x); break;
+    }
+    memcpy(out, &z, sizeof(z));
+}
+extern "C" void he_f12_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    if (curve == 0) t_f12<BN254>(op, a, b, out);
+    else if (curve == 1) t_f12<BLS381>(op, a, b, out);
+    else t_f12<BLS377>(op, a, b, out);
+}

@@ -1,0 +1,116 @@
+/* libb200math -- C ABI of the B200 (sm_100a) backend for IBM/mathlib's batched pairing and G1 hot path.
+ *
+ * This is the drop-in boundary: what a `driver/b200` Go package binds through cgo (see INTEGRATION.md and
+ * driver/b200/*.go) to implement mathlib's `driver.Curve` / `driver.G1` hot-path methods
+ * (reference driver/math.go:49-180 and :249-288).  Plain pointers and sizes only; no torch / CUDA types.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative B200_ERR_* code otherwise; b200_last_error() gives the
+ *    thread-local message.  The library never aborts the process; the Go wrapper turns a non-zero return
+ *    into the same panic the reference drivers raise (reference driver/gurvy/bn254.go:249-251).
+ *  - Every function is re-entrant; concurrent calls that share read-only inputs are legal (the reference
+ *    benchmarks call one curve from many goroutines: perf_test.go:392-405).
+ *  - Host buffers belong to the caller and are only read / written during the call (cgo pointer rules).
+ *  - `curve` is the mathlib CurveID (reference math.go:70-103): 1 BN254, 3 BLS12_381 (kilic semantics),
+ *    4 BLS12_377_GURVY, 5 BLS12_381_GURVY, 6 BLS12_381_BBS (kilic semantics), 7 BLS12_381_BBS_GURVY.
+ *    "kilic semantics": Pairing/Pairing2 include the final exponentiation and FExp is the identity
+ *    (reference driver/kilic/bls12-381.go:260-281); gurvy: Pairing* is the raw Miller value and FExp
+ *    exponentiates (reference driver/gurvy/bls12381/bls12-381.go:448-468).
+ *
+ * Element encodings (selected per call with B200_IN_* / B200_OUT_* flags)
+ *  - BYTES (default): exactly what the reference's Bytes() returns / New*FromBytes() accepts
+ *      Fp   : FpBytes big-endian canonical (32 for BN254, 48 for BLS12-381/377)
+ *      G1   : X || Y                      (reference bn254.go:76-80; kilic/bls12-381.go:74-78), infinity flagged
+ *      G2   : X.A1 || X.A0 || Y.A1 || Y.A0 (reference bn254.go:147-151)
+ *      Gt   : 12 Fp, C1.B2.A1 first ... C0.B0.A0 last (reference bn254.go:216-220, kilic/bls12-381.go:224-231)
+ *      Zr   : 32 bytes big-endian (reference driver/common/big.go:101-113); any value < 2^256 is accepted and
+ *             used mod r
+ *  - MONT: in-memory layout of gnark-crypto / kilic elements -- little-endian 32-bit limbs (== 64-bit limbs on
+ *      little-endian hosts) in Montgomery form, R = 2^256 / 2^384 (reference driver/gurvy/custom.go:30-40 shows the
+ *      two libraries share it).  G1 = X|Y, G2 = X.A0|X.A1|Y.A0|Y.A1, Gt = C0.B0.A0|C0.B0.A1|C0.B1.A0|...|C1.B2.A1,
+ *      infinity = all zero.  Scalars stay 32-byte big-endian.
+ */
+#ifndef B200_H
+#define B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* curve ids == mathlib CurveID (reference math.go:70-103) */
+#define B200_BN254 1
+#define B200_BLS12_381 3
+#define B200_BLS12_377_GURVY 4
+#define B200_BLS12_381_GURVY 5
+#define B200_BLS12_381_BBS 6
+#define B200_BLS12_381_BBS_GURVY 7
+
+/* flags */
+#define B200_FEXP 0x1u           /* pairing*: also apply the final exponentiation (no-op for kilic ids) */
+#define B200_IN_MONT 0x2u        /* group/Gt inputs are MONT limbs instead of BYTES */
+#define B200_OUT_MONT 0x4u       /* group/Gt outputs are MONT limbs instead of BYTES */
+#define B200_OUT_UNITY_ONLY 0x8u /* pairing / fexp: write one byte per item: 1 if the result is 1 (Gt.IsUnity), else 0 */
+#define B200_DEVICE_PTRS 0x10u   /* all buffers are device pointers on the current device (no copies, async on the
+                                    stream set with b200_set_stream; caller synchronises) */
+
+/* error codes */
+#define B200_OK 0
+#define B200_ERR_CUDA -1     /* CUDA runtime error (message has the cudaError string) */
+#define B200_ERR_ARG -2      /* bad curve id / null pointer / unsupported flag combination */
+#define B200_ERR_ENCODING -3 /* an input coordinate is not a canonical field element (>= p) */
+#define B200_ERR_NOGPU -4    /* no CUDA device / library not initialised: there is NO CPU fallback */
+
+/* Library lifetime.  device_mask bit i selects CUDA device i (0 = all visible devices). */
+int b200_init(uint32_t device_mask);
+void b200_shutdown(void);
+const char* b200_last_error(void);
+int b200_device_count(void);
+/* Per calling thread: device used by subsequent calls (default: first device of the mask; batch calls with host
+   buffers split across ALL devices of the mask when b200_set_device was never called on the thread). */
+int b200_set_device(int device);
+/* Per calling thread: CUDA stream (cudaStream_t as void*) used with B200_DEVICE_PTRS; NULL = default stream. */
+int b200_set_stream(void* cuda_stream);
+
+/* sizes in bytes of the BYTES / MONT encodings for a curve (FpBytes = 32 or 48) */
+int b200_fp_bytes(int curve);
+
+/* driver.Curve.Pairing(G2, G1) for n independent pairs (reference driver/math.go:51).
+   g1: n G1 elements, g2: n G2 elements, gt_out: n Gt elements (or n bytes with B200_OUT_UNITY_ONLY). */
+int b200_pairing_batch(int curve, size_t n, const void* g1, const void* g2, void* gt_out, uint32_t flags);
+
+/* driver.Curve.Pairing2(p2a, p2b, p1a, p1b) = e(p2a,p1a)*e(p2b,p1b) with one shared squaring chain
+   (reference driver/math.go:54; facade argument reorder math.go:869-871). */
+int b200_pairing2_batch(int curve, size_t n, const void* g1a, const void* g2a, const void* g1b, const void* g2b,
+                        void* gt_out, uint32_t flags);
+
+/* driver.Curve.FExp (reference driver/math.go:57).  Identity copy for kilic-semantics ids. */
+int b200_fexp_batch(int curve, size_t n, const void* gt_in, void* gt_out, uint32_t flags);
+
+/* driver.G1.Mul (reference driver/math.go:260): out[i] = [scalars[i]] pts[i], affine. */
+int b200_g1_mul_batch(int curve, size_t n, const void* pts, const void* scalars_be32, void* out, uint32_t flags);
+
+/* driver.G1.Mul2 / Mul2InPlace (reference driver/math.go:263-266): out[i] = [e[i]]P[i] + [f[i]]Q[i]. */
+int b200_g1_mul2_batch(int curve, size_t n, const void* P, const void* e_be32, const void* Q, const void* f_be32,
+                       void* out, uint32_t flags);
+
+/* driver.Curve.MultiScalarMul (reference driver/math.go:170): out = sum_i [scalars[i]] pts[i], one affine G1.
+   n == 0 gives infinity. */
+int b200_g1_msm(int curve, size_t n, const void* pts, const void* scalars_be32, void* out, uint32_t flags);
+
+/* Resident base points: upload once, run many MSMs against them (scalars only cross PCIe). */
+int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint64_t* handle);
+int b200_g1_msm_resident(uint64_t handle, size_t n, const void* scalars_be32, void* out, uint32_t flags);
+int b200_bases_free(uint64_t handle);
+
+/* sum of n G1 points (used to combine per-GPU MSM partial sums; n is small). */
+int b200_g1_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags);
+
+/* Number of kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
+uint64_t b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_H */

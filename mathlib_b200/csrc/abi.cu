@@ -1,0 +1,606 @@
+// C ABI of libb200math (include/b200.h): argument checking, device workspaces, host<->device staging,
+// index-split over the GPUs of one box, and the tiny MSM partial-sum combine.  All arithmetic happens in
+// the sm_100a kernels reached through the per-curve tables (launch.cuh); there is no CPU fallback.
+#include "../../include/b200.h"
+#include "launch.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <map>
+
+namespace b200 {
+std::atomic<uint64_t> g_launch_count{0};
+}
+using namespace b200;
+
+namespace {
+
+thread_local std::string t_err;
+thread_local int t_device = -1;          // -1: not pinned by b200_set_device
+thread_local cudaStream_t t_stream = nullptr;
+
+std::mutex g_mu;
+bool g_inited = false;
+std::vector<int> g_devices;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+#define CU(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (x);                                                                   \
+        if (_e != cudaSuccess) return fail(B200_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct CurveInfo {
+    const CurveVTable* vt;
+    bool kilic;     // Pairing includes FExp; FExp is the identity
+};
+bool curve_info(int curve, CurveInfo* ci) {
+    switch (curve) {
+        case B200_BN254: *ci = {vtable_bn254(), false}; return true;
+        case B200_BLS12_381: case B200_BLS12_381_BBS: *ci = {vtable_bls381(), true}; return true;
+        case B200_BLS12_381_GURVY: case B200_BLS12_381_BBS_GURVY: *ci = {vtable_bls381(), false}; return true;
+        case B200_BLS12_377_GURVY: *ci = {vtable_bls377(), false}; return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-device workspaces (grow-only slab + stream + error flag), pooled so concurrent callers never share one
+// ---------------------------------------------------------------------------------------------
+struct Workspace {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t* buf = nullptr;
+    size_t cap = 0;
+    int* d_err = nullptr;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (buf) { cudaFree(buf); buf = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + (1 << 20);
+        cudaError_t e = cudaMalloc(&buf, want);
+        if (e != cudaSuccess) return fail(B200_ERR_CUDA, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+};
+std::map<int, std::vector<Workspace*>> g_free_ws;
+
+Workspace* ws_acquire(int dev) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto& v = g_free_ws[dev];
+        if (!v.empty()) { Workspace* w = v.back(); v.pop_back(); return w; }
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    Workspace* w = new Workspace();
+    w->dev = dev;
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return nullptr; }
+    if (cudaMalloc(&w->d_err, sizeof(int)) != cudaSuccess) { delete w; return nullptr; }
+    return w;
+}
+void ws_release(Workspace* w) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_free_ws[w->dev].push_back(w);
+}
+struct WsGuard {
+    Workspace* w;
+    explicit WsGuard(int dev) : w(ws_acquire(dev)) {}
+    ~WsGuard() { if (w) ws_release(w); }
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int ensure_init() {
+    if (g_inited) return 0;
+    return b200_init(0);
+}
+int current_device() { return t_device >= 0 ? t_device : g_devices[0]; }
+
+// devices a host-buffer batch call is split over
+std::vector<int> split_devices(size_t n, size_t min_per_dev) {
+    std::vector<int> d;
+    if (t_device >= 0 || g_devices.size() == 1 || n < 2 * min_per_dev) { d.push_back(current_device()); return d; }
+    size_t k = g_devices.size();
+    while (k > 1 && n / k < min_per_dev) k--;
+    d.assign(g_devices.begin(), g_devices.begin() + k);
+    return d;
+}
+
+// run fn(dev, lo, hi) over contiguous index ranges, one host thread per device
+template <class Fn>
+int run_split(const std::vector<int>& devs, size_t n, Fn fn) {
+    if (devs.size() == 1) return fn(devs[0], (size_t)0, n);
+    std::vector<std::thread> th;
+    std::vector<int> rc(devs.size(), 0);
+    std::vector<std::string> msg(devs.size());
+    for (size_t k = 0; k < devs.size(); k++) {
+        size_t lo = n * k / devs.size(), hi = n * (k + 1) / devs.size();
+        th.emplace_back([&, k, lo, hi]() {
+            rc[k] = fn(devs[k], lo, hi);
+            if (rc[k]) msg[k] = t_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < devs.size(); k++)
+        if (rc[k]) { t_err = msg[k]; return rc[k]; }
+    return 0;
+}
+
+struct Piece { const void* host; size_t elem; uint8_t* dev; };
+
+// stage inputs, run, fetch output for the index range [lo,hi) on one device
+template <class LaunchFn>
+int staged_call(int dev, size_t lo, size_t hi, std::vector<Piece> ins, void* out_host, size_t out_elem,
+                LaunchFn launch) {
+    size_t m = hi - lo;
+    if (m == 0) return 0;
+    WsGuard g(dev);
+    if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d: %s", dev,
+                          cudaGetErrorString(cudaGetLastError()));
+    Workspace& w = *g.w;
+    CU(cudaSetDevice(dev));
+    size_t total = 0;
+    for (auto& p : ins) total += align_up(p.elem * m);
+    total += align_up(out_elem * m);
+    if (int rc = w.reserve(total)) return rc;
+    size_t off = 0;
+    for (auto& p : ins) {
+        p.dev = w.buf + off;
+        CU(cudaMemcpyAsync(p.dev, (const uint8_t*)p.host + lo * p.elem, p.elem * m, cudaMemcpyHostToDevice, w.stream));
+        off += align_up(p.elem * m);
+    }
+    uint8_t* d_out = w.buf + off;
+    CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
+    cudaError_t e = launch(m, ins, d_out, w.d_err, w.stream);
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    int h_err = 0;
+    CU(cudaMemcpyAsync((uint8_t*)out_host + lo * out_elem, d_out, out_elem * m, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
+    return 0;
+}
+
+int* device_err_flag(int dev) {      // scratch flag for DEVICE_PTRS calls (never read back)
+    static std::map<int, int*> flags;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = flags.find(dev);
+    if (it != flags.end()) return it->second;
+    int* p = nullptr;
+    cudaSetDevice(dev);
+    cudaMalloc(&p, sizeof(int));
+    cudaMemset(p, 0, sizeof(int));
+    flags[dev] = p;
+    return p;
+}
+
+uint32_t kernel_flags(uint32_t flags) { return flags & (B200_FEXP | B200_IN_MONT | B200_OUT_MONT | B200_OUT_UNITY_ONLY); }
+
+struct Bases {
+    int curve; int dev; size_t n; void* pts;
+};
+std::map<uint64_t, Bases> g_bases;
+uint64_t g_next_handle = 1;
+
+// carve the MSM workspace; returns bytes needed (buf may be null to size only)
+size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_points, uint8_t* base, MsmBuffers* b,
+                 uint8_t** scalars_dev, uint8_t** pts_in_dev, size_t pts_in_bytes, uint8_t** out_dev) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+    size_t nb = (size_t)pl.W * pl.B;
+    b->points = need_points ? take(n * vt->aff_size) : nullptr;
+    b->digits = (uint32_t*)take((size_t)pl.W * n * 4);
+    b->sorted = (uint32_t*)take((size_t)pl.W * n * 4);
+    b->counts = (uint32_t*)take(nb * 4);
+    b->offsets = (uint32_t*)take(nb * 4);
+    b->cursor = (uint32_t*)take(nb * 4);
+    b->buckets = take(nb * vt->xyzz_size);
+    b->chunks = take((size_t)pl.W * pl.nchunks * vt->xyzz_size);
+    b->windows = take((size_t)pl.W * vt->xyzz_size);
+    if (scalars_dev) *scalars_dev = take(n * 32);
+    if (pts_in_dev) *pts_in_dev = take(pts_in_bytes);
+    if (out_dev) *out_dev = take(2 * (size_t)vt->fp_bytes);
+    return off;
+}
+
+// MSM of host points/scalars [lo,hi) on one device -> one affine point written to out_host
+int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const void* pts, const void* resident_pts,
+                   const void* scalars, void* out_host, uint32_t flags) {
+    const CurveVTable* vt = ci.vt;
+    size_t m = hi - lo;
+    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    WsGuard g(dev);
+    if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
+    Workspace& w = *g.w;
+    CU(cudaSetDevice(dev));
+    MsmPlan pl = msm_plan(m ? m : 1, vt->scalar_bits);
+    MsmBuffers b;
+    uint8_t *d_sc = nullptr, *d_pin = nullptr, *d_out = nullptr;
+    bool need_points = resident_pts == nullptr;
+    size_t need = msm_carve(vt, pl, m, need_points, nullptr, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out);
+    if (int rc = w.reserve(need)) return rc;
+    msm_carve(vt, pl, m, need_points, w.buf, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out);
+    CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
+    const void* prepared = resident_pts;
+    if (m) {
+        CU(cudaMemcpyAsync(d_sc, (const uint8_t*)scalars + lo * 32, m * 32, cudaMemcpyHostToDevice, w.stream));
+        if (need_points) {
+            CU(cudaMemcpyAsync(d_pin, (const uint8_t*)pts + lo * g1sz, m * g1sz, cudaMemcpyHostToDevice, w.stream));
+            CU(vt->msm_points(m, d_pin, b.points, kernel_flags(flags), w.d_err, w.stream));
+            prepared = b.points;
+        } else {
+            prepared = (const uint8_t*)resident_pts + lo * vt->aff_size;
+        }
+    }
+    CU(vt->msm(m, prepared, d_sc, d_out, kernel_flags(flags), pl, b, w.stream));
+    int h_err = 0;
+    CU(cudaMemcpyAsync(out_host, d_out, g1sz, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int b200_init(uint32_t device_mask) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        g_inited = false;
+        return fail(B200_ERR_NOGPU, "no CUDA device available (%s); libb200math has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    g_devices.clear();
+    for (int i = 0; i < cnt && i < 32; i++)
+        if (device_mask == 0 || (device_mask >> i) & 1) g_devices.push_back(i);
+    if (g_devices.empty()) return fail(B200_ERR_ARG, "device mask 0x%x selects none of the %d devices", device_mask, cnt);
+    g_inited = true;
+    return 0;
+}
+
+void b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_free_ws) {
+        cudaSetDevice(kv.first);
+        for (Workspace* w : kv.second) {
+            if (w->buf) cudaFree(w->buf);
+            if (w->d_err) cudaFree(w->d_err);
+            if (w->stream) cudaStreamDestroy(w->stream);
+            delete w;
+        }
+    }
+    g_free_ws.clear();
+    for (auto& kv : g_bases) { cudaSetDevice(kv.second.dev); cudaFree(kv.second.pts); }
+    g_bases.clear();
+    g_inited = false;
+}
+
+const char* b200_last_error(void) { return t_err.c_str(); }
+
+int b200_device_count(void) {
+    if (ensure_init()) return 0;
+    return (int)g_devices.size();
+}
+
+int b200_set_device(int device) {
+    if (int rc = ensure_init()) return rc;
+    int cnt = 0;
+    cudaGetDeviceCount(&cnt);
+    if (device < 0 || device >= cnt) return fail(B200_ERR_ARG, "device %d out of range (%d devices)", device, cnt);
+    t_device = device;
+    return 0;
+}
+
+int b200_set_stream(void* cuda_stream) {
+    t_stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int b200_fp_bytes(int curve) {
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    return ci.vt->fp_bytes;
+}
+
+uint64_t b200_launch_count(void) { return g_launch_count.load(); }
+
+static int pairing_common(int curve, int np, size_t n, const void* g1a, const void* g2a, const void* g1b,
+                          const void* g2b, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n == 0) return 0;
+    if (!g1a || !g2a || !out || (np == 2 && (!g1b || !g2b))) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    uint32_t kf = kernel_flags(flags);
+    if (ci.kilic) kf |= B200_FEXP;
+    size_t fb = vt->fp_bytes, g1sz = 2 * fb, g2sz = 4 * fb;
+    size_t osz = (flags & B200_OUT_UNITY_ONLY) ? 1 : 12 * fb;
+    if (flags & B200_DEVICE_PTRS) {
+        int dev = current_device();
+        CU(cudaSetDevice(dev));
+        CU(vt->pairing(np, n, (const uint8_t*)g1a, (const uint8_t*)g2a, (const uint8_t*)g1b, (const uint8_t*)g2b,
+                       (uint8_t*)out, kf, device_err_flag(dev), t_stream));
+        return 0;
+    }
+    auto devs = split_devices(n, 256);
+    return run_split(devs, n, [&](int dev, size_t lo, size_t hi) {
+        std::vector<Piece> ins = {{g1a, g1sz, nullptr}, {g2a, g2sz, nullptr}};
+        if (np == 2) { ins.push_back({g1b, g1sz, nullptr}); ins.push_back({g2b, g2sz, nullptr}); }
+        return staged_call(dev, lo, hi, ins, out, osz,
+                           [&](size_t m, std::vector<Piece>& p, uint8_t* d_out, int* d_err, cudaStream_t s) {
+                               return vt->pairing(np, m, p[0].dev, p[1].dev, np == 2 ? p[2].dev : nullptr,
+                                                  np == 2 ? p[3].dev : nullptr, d_out, kf, d_err, s);
+                           });
+    });
+}
+
+int b200_pairing_batch(int curve, size_t n, const void* g1, const void* g2, void* gt_out, uint32_t flags) {
+    return pairing_common(curve, 1, n, g1, g2, nullptr, nullptr, gt_out, flags);
+}
+
+int b200_pairing2_batch(int curve, size_t n, const void* g1a, const void* g2a, const void* g1b, const void* g2b,
+                        void* gt_out, uint32_t flags) {
+    return pairing_common(curve, 2, n, g1a, g2a, g1b, g2b, gt_out, flags);
+}
+
+int b200_fexp_batch(int curve, size_t n, const void* gt_in, void* gt_out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n == 0) return 0;
+    if (!gt_in || !gt_out) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    // driver.Curve.FExp always exponentiates for gurvy ids and is the identity for kilic ids
+    uint32_t kf = (kernel_flags(flags) & ~B200_FEXP) | (ci.kilic ? 0u : B200_FEXP);
+    size_t gtsz = 12 * (size_t)vt->fp_bytes;
+    size_t osz = (flags & B200_OUT_UNITY_ONLY) ? 1 : gtsz;
+    if (flags & B200_DEVICE_PTRS) {
+        int dev = current_device();
+        CU(cudaSetDevice(dev));
+        CU(vt->fexp(n, (const uint8_t*)gt_in, (uint8_t*)gt_out, kf, device_err_flag(dev), t_stream));
+        return 0;
+    }
+    auto devs = split_devices(n, 256);
+    return run_split(devs, n, [&](int dev, size_t lo, size_t hi) {
+        std::vector<Piece> ins = {{gt_in, gtsz, nullptr}};
+        return staged_call(dev, lo, hi, ins, gt_out, osz,
+                           [&](size_t m, std::vector<Piece>& p, uint8_t* d_out, int* d_err, cudaStream_t s) {
+                               return vt->fexp(m, p[0].dev, d_out, kf, d_err, s);
+                           });
+    });
+}
+
+int b200_g1_mul_batch(int curve, size_t n, const void* pts, const void* scalars, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n == 0) return 0;
+    if (!pts || !scalars || !out) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    uint32_t kf = kernel_flags(flags);
+    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    if (flags & B200_DEVICE_PTRS) {
+        int dev = current_device();
+        CU(cudaSetDevice(dev));
+        CU(vt->g1_mul(n, (const uint8_t*)pts, (const uint8_t*)scalars, (uint8_t*)out, kf, device_err_flag(dev), t_stream));
+        return 0;
+    }
+    auto devs = split_devices(n, 1024);
+    return run_split(devs, n, [&](int dev, size_t lo, size_t hi) {
+        std::vector<Piece> ins = {{pts, g1sz, nullptr}, {scalars, 32, nullptr}};
+        return staged_call(dev, lo, hi, ins, out, g1sz,
+                           [&](size_t m, std::vector<Piece>& p, uint8_t* d_out, int* d_err, cudaStream_t s) {
+                               return vt->g1_mul(m, p[0].dev, p[1].dev, d_out, kf, d_err, s);
+                           });
+    });
+}
+
+int b200_g1_mul2_batch(int curve, size_t n, const void* P, const void* e, const void* Q, const void* f, void* out,
+                       uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n == 0) return 0;
+    if (!P || !e || !Q || !f || !out) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    uint32_t kf = kernel_flags(flags);
+    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    if (flags & B200_DEVICE_PTRS) {
+        int dev = current_device();
+        CU(cudaSetDevice(dev));
+        CU(vt->g1_mul2(n, (const uint8_t*)P, (const uint8_t*)e, (const uint8_t*)Q, (const uint8_t*)f, (uint8_t*)out, kf,
+                       device_err_flag(dev), t_stream));
+        return 0;
+    }
+    auto devs = split_devices(n, 1024);
+    return run_split(devs, n, [&](int dev, size_t lo, size_t hi) {
+        std::vector<Piece> ins = {{P, g1sz, nullptr}, {e, 32, nullptr}, {Q, g1sz, nullptr}, {f, 32, nullptr}};
+        return staged_call(dev, lo, hi, ins, out, g1sz,
+                           [&](size_t m, std::vector<Piece>& p, uint8_t* d_out, int* d_err, cudaStream_t s) {
+                               return vt->g1_mul2(m, p[0].dev, p[1].dev, p[2].dev, p[3].dev, d_out, kf, d_err, s);
+                           });
+    });
+}
+
+int b200_g1_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out || (n && !pts)) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    uint32_t kf = kernel_flags(flags);
+    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    if (flags & B200_DEVICE_PTRS) {
+        CU(vt->g1_sum(n, (const uint8_t*)pts, (uint8_t*)out, kf, device_err_flag(dev), t_stream));
+        return 0;
+    }
+    WsGuard g(dev);
+    if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
+    Workspace& w = *g.w;
+    if (int rc = w.reserve(align_up(n * g1sz) + g1sz)) return rc;
+    uint8_t* d_out = w.buf + align_up(n * g1sz);
+    if (n) CU(cudaMemcpyAsync(w.buf, pts, n * g1sz, cudaMemcpyHostToDevice, w.stream));
+    CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
+    CU(vt->g1_sum(n, w.buf, d_out, kf, w.d_err, w.stream));
+    int h_err = 0;
+    CU(cudaMemcpyAsync(out, d_out, g1sz, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
+    return 0;
+}
+
+static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool prepared, const void* scalars,
+                           void* out, uint32_t flags) {
+    // device-pointer MSM: the workspace comes from the pool and is held until the stream is synchronised by the
+    // caller, so it is acquired per thread and kept (thread-local) instead of being released.
+    thread_local std::map<int, Workspace*> t_ws;
+    const CurveVTable* vt = ci.vt;
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    Workspace*& w = t_ws[dev];
+    if (!w) w = ws_acquire(dev);
+    if (!w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
+    MsmPlan pl = msm_plan(n ? n : 1, vt->scalar_bits);
+    MsmBuffers b;
+    bool need_points = !prepared;
+    size_t need = msm_carve(vt, pl, n, need_points, nullptr, &b, nullptr, nullptr, 0, nullptr);
+    if (need > w->cap) {
+        CU(cudaStreamSynchronize(t_stream));     // earlier async work may still use the old slab
+        if (int rc = w->reserve(need)) return rc;
+    }
+    msm_carve(vt, pl, n, need_points, w->buf, &b, nullptr, nullptr, 0, nullptr);
+    const void* prep = pts;
+    if (need_points && n) {
+        CU(vt->msm_points(n, (const uint8_t*)pts, b.points, kernel_flags(flags), w->d_err, t_stream));
+        prep = b.points;
+    }
+    CU(vt->msm(n, prep, (const uint8_t*)scalars, (uint8_t*)out, kernel_flags(flags), pl, b, t_stream));
+    return 0;
+}
+
+int b200_g1_msm(int curve, size_t n, const void* pts, const void* scalars, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out || (n && (!pts || !scalars))) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    if (flags & B200_DEVICE_PTRS) return msm_device_ptrs(ci, n, pts, false, scalars, out, flags);
+    auto devs = split_devices(n, (size_t)1 << 16);
+    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    if (devs.size() == 1) return msm_host_range(ci, devs[0], 0, n, pts, nullptr, scalars, out, flags);
+    // range-split: one partial sum per GPU, then a tiny combine on the first GPU
+    std::vector<uint8_t> partial(devs.size() * g1sz);
+    size_t k = 0;
+    std::vector<size_t> los, his;
+    for (size_t d = 0; d < devs.size(); d++) { los.push_back(n * d / devs.size()); his.push_back(n * (d + 1) / devs.size()); }
+    std::vector<std::thread> th;
+    std::vector<int> rc(devs.size(), 0);
+    std::vector<std::string> msg(devs.size());
+    uint32_t pflags = (flags & ~B200_OUT_MONT) | B200_OUT_MONT;   // partials travel as MONT limbs
+    for (k = 0; k < devs.size(); k++)
+        th.emplace_back([&, k]() {
+            rc[k] = msm_host_range(ci, devs[k], los[k], his[k], pts, nullptr, scalars, partial.data() + k * g1sz, pflags);
+            if (rc[k]) msg[k] = t_err;
+        });
+    for (auto& t : th) t.join();
+    for (k = 0; k < devs.size(); k++)
+        if (rc[k]) { t_err = msg[k]; return rc[k]; }
+    int saved = t_device;
+    t_device = devs[0];
+    int r = b200_g1_sum(curve, devs.size(), partial.data(), out, (flags & B200_OUT_MONT) | B200_IN_MONT);
+    t_device = saved;
+    return r;
+}
+
+int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint64_t* handle) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!handle || (n && !pts)) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    void* d_pts = nullptr;
+    CU(cudaMalloc(&d_pts, (n ? n : 1) * vt->aff_size));
+    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    if (n) {
+        if (flags & B200_DEVICE_PTRS) {
+            CU(vt->msm_points(n, (const uint8_t*)pts, d_pts, kernel_flags(flags), device_err_flag(dev), t_stream));
+            CU(cudaStreamSynchronize(t_stream));
+        } else {
+            WsGuard g(dev);
+            if (!g.w) { cudaFree(d_pts); return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev); }
+            Workspace& w = *g.w;
+            if (int rc = w.reserve(n * g1sz)) { cudaFree(d_pts); return rc; }
+            CU(cudaMemcpyAsync(w.buf, pts, n * g1sz, cudaMemcpyHostToDevice, w.stream));
+            CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
+            CU(vt->msm_points(n, w.buf, d_pts, kernel_flags(flags), w.d_err, w.stream));
+            int h_err = 0;
+            CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+            CU(cudaStreamSynchronize(w.stream));
+            if (h_err) { cudaFree(d_pts); return fail(B200_ERR_ENCODING, "input is not a canonical element encoding"); }
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t h = g_next_handle++;
+    g_bases[h] = {curve, dev, n, d_pts};
+    *handle = h;
+    return 0;
+}
+
+int b200_g1_msm_resident(uint64_t handle, size_t n, const void* scalars, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    Bases bs;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_bases.find(handle);
+        if (it == g_bases.end()) return fail(B200_ERR_ARG, "unknown bases handle %llu", (unsigned long long)handle);
+        bs = it->second;
+    }
+    if (n > bs.n) return fail(B200_ERR_ARG, "n=%zu exceeds the %zu resident bases", n, bs.n);
+    if (!out || (n && !scalars)) return fail(B200_ERR_ARG, "null buffer");
+    CurveInfo ci;
+    curve_info(bs.curve, &ci);
+    if (flags & B200_DEVICE_PTRS) {
+        int saved = t_device;
+        t_device = bs.dev;
+        int r = msm_device_ptrs(ci, n, bs.pts, true, scalars, out, flags);
+        t_device = saved;
+        return r;
+    }
+    return msm_host_range(ci, bs.dev, 0, n, nullptr, bs.pts, scalars, out, flags);
+}
+
+int b200_bases_free(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bases.find(handle);
+    if (it == g_bases.end()) return fail(B200_ERR_ARG, "unknown bases handle %llu", (unsigned long long)handle);
+    cudaSetDevice(it->second.dev);
+    cudaFree(it->second.pts);
+    g_bases.erase(it);
+    return 0;
+}
+
+}  // extern "C"

@@ -31,7 +31,7 @@ B200_DEFINE_CONSTS(BLS377, 12)
 
 #if defined(__CUDACC__)
 #define B200_DEFINE_DCONSTS(NAME, NL)                                                       \
-    __device__ __constant__ CurveConsts<NL> D_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2,    \
+    static __device__ __constant__ CurveConsts<NL> D_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2,    \
                                                         NAME##_B, NAME##_B3, NAME##_BTW,    \
                                                         NAME##_ORDER, NAME##_FROB1,         \
                                                         NAME##_FROB2, NAME##_FROB3};

@@ -1,0 +1,169 @@
+// G1 arithmetic in extended-Jacobian (XYZZ) coordinates for curves y^2 = x^3 + b (a = 0).
+//
+// Replaces what the reference adapters forward to gnark-crypto / kilic:
+//   G1.Mul            reference driver/gurvy/bn254.go:49-54, bls12-377.go:48-53,
+//                     bls12381/bls12-381.go:238-247, driver/kilic/bls12-381.go:40-50
+//   G1.Mul2 / InPlace reference bn254.go:56-70, bls12-381.go:249-280 + 869-937, kilic/bls12-381.go:52-66
+//   MultiScalarMul    reference bn254.go:232-245, bls12-377.go:229-242, bls12-381.go:766-783
+// Results are canonical group elements (affine, (0,0) = infinity as in gnark), so any correct
+// addition chain is byte-exact.  The adders are complete: equal inputs fall through to
+// the doubling, opposite inputs to infinity.
+#pragma once
+#include "curves.cuh"
+
+namespace b200 {
+
+template <int N> struct G1Affine { Fp<N> x, y; };                    // (0,0) = infinity
+template <int N> struct G1XYZZ { Fp<N> x, y, zz, zzz; };             // zz == 0  <=> infinity
+
+template <class C>
+struct G1Ops {
+    static constexpr int N = C::N;
+    typedef FpOps<C> F;
+    typedef Fp<N> E;
+    typedef G1Affine<N> Aff;
+    typedef G1XYZZ<N> Pt;
+
+    static B200_HD bool aff_is_inf(const Aff& a) { return F::is_zero(a.x) && F::is_zero(a.y); }
+    static B200_HD bool is_inf(const Pt& p) { return F::is_zero(p.zz); }
+    static B200_HD void set_inf(Pt& p) { F::zero(p.x); F::zero(p.y); F::zero(p.zz); F::zero(p.zzz); }
+    static B200_HD void from_affine(Pt& p, const Aff& a) {
+        if (aff_is_inf(a)) { set_inf(p); return; }
+        p.x = a.x; p.y = a.y; F::one(p.zz); F::one(p.zzz);
+    }
+    static B200_HD void neg_affine(Aff& r, const Aff& a) { r.x = a.x; F::neg(r.y, a.y); }
+    static B200_HD void neg(Pt& r, const Pt& a) { r.x = a.x; F::neg(r.y, a.y); r.zz = a.zz; r.zzz = a.zzz; }
+
+    // p <- 2a for affine a (mdbl-2008-s-1)
+    static B200_HD void dbl_affine(Pt& p, const Aff& a) {
+        if (aff_is_inf(a) || F::is_zero(a.y)) { set_inf(p); return; }
+        E U, V, W, S, M, t;
+        F::dbl(U, a.y);
+        F::sqr(V, U);
+        F::mul(W, U, V);
+        F::mul(S, a.x, V);
+        F::sqr(M, a.x);
+        F::dbl(t, M); F::add(M, M, t);
+        F::sqr(p.x, M);
+        F::sub(p.x, p.x, S); F::sub(p.x, p.x, S);
+        F::sub(t, S, p.x);
+        F::mul(t, M, t);
+        F::mul(U, W, a.y);
+        F::sub(p.y, t, U);
+        p.zz = V;
+        p.zzz = W;
+    }
+    // p <- 2p (dbl-2008-s-1)
+    static B200_HD_NOINLINE void dbl(Pt& p) {
+        if (is_inf(p)) return;
+        E U, V, W, S, M, t;
+        F::dbl(U, p.y);
+        F::sqr(V, U);
+        F::mul(W, U, V);
+        F::mul(S, p.x, V);
+        F::sqr(M, p.x);
+        F::dbl(t, M); F::add(M, M, t);
+        F::mul(U, W, p.y);            // W*Y1
+        F::sqr(p.x, M);
+        F::sub(p.x, p.x, S); F::sub(p.x, p.x, S);
+        F::sub(t, S, p.x);
+        F::mul(t, M, t);
+        F::sub(p.y, t, U);
+        F::mul(p.zz, V, p.zz);
+        F::mul(p.zzz, W, p.zzz);
+    }
+    // p <- p + a, a affine (madd-2008-s), complete
+    static B200_HD_NOINLINE void madd(Pt& p, const Aff& a) {
+        if (aff_is_inf(a)) return;
+        if (is_inf(p)) { from_affine(p, a); return; }
+        E U2, S2, Pp, R, PP, PPP, Q, t;
+        F::mul(U2, a.x, p.zz);
+        F::mul(S2, a.y, p.zzz);
+        F::sub(Pp, U2, p.x);
+        F::sub(R, S2, p.y);
+        if (F::is_zero(Pp)) {
+            if (F::is_zero(R)) dbl_affine(p, a); else set_inf(p);
+            return;
+        }
+        F::sqr(PP, Pp);
+        F::mul(PPP, Pp, PP);
+        F::mul(Q, p.x, PP);
+        F::sqr(t, R);
+        F::sub(t, t, PPP); F::sub(t, t, Q); F::sub(t, t, Q);   // X3
+        F::sub(Q, Q, t);
+        F::mul(Q, R, Q);
+        F::mul(S2, p.y, PPP);
+        F::sub(p.y, Q, S2);
+        p.x = t;
+        F::mul(p.zz, p.zz, PP);
+        F::mul(p.zzz, p.zzz, PPP);
+    }
+    // p <- p + q (add-2008-s), complete
+    static B200_HD_NOINLINE void add(Pt& p, const Pt& q) {
+        if (is_inf(q)) return;
+        if (is_inf(p)) { p = q; return; }
+        E U1, U2, S1, S2, Pp, R, PP, PPP, Q, t;
+        F::mul(U1, p.x, q.zz);
+        F::mul(U2, q.x, p.zz);
+        F::mul(S1, p.y, q.zzz);
+        F::mul(S2, q.y, p.zzz);
+        F::sub(Pp, U2, U1);
+        F::sub(R, S2, S1);
+        if (F::is_zero(Pp)) {
+            if (F::is_zero(R)) dbl(p); else set_inf(p);
+            return;
+        }
+        F::sqr(PP, Pp);
+        F::mul(PPP, Pp, PP);
+        F::mul(Q, U1, PP);
+        F::sqr(t, R);
+        F::sub(t, t, PPP); F::sub(t, t, Q); F::sub(t, t, Q);   // X3
+        F::sub(Q, Q, t);
+        F::mul(Q, R, Q);
+        F::mul(S1, S1, PPP);
+        F::sub(p.y, Q, S1);
+        p.x = t;
+        F::mul(p.zz, p.zz, q.zz);
+        F::mul(p.zz, p.zz, PP);
+        F::mul(p.zzz, p.zzz, q.zzz);
+        F::mul(p.zzz, p.zzz, PPP);
+    }
+    // affine (x,y) = (X/ZZ, Y/ZZZ); infinity -> (0,0)
+    static B200_HD void to_affine(Aff& a, const Pt& p) {
+        if (is_inf(p)) { F::zero(a.x); F::zero(a.y); return; }
+        E t, i;
+        F::mul(t, p.zz, p.zzz);
+        F::inv(i, t);
+        F::mul(t, i, p.zzz);      // 1/ZZ
+        F::mul(a.x, p.x, t);
+        F::mul(t, i, p.zz);       // 1/ZZZ
+        F::mul(a.y, p.y, t);
+    }
+
+    // scalar: 8 little-endian 32-bit words (any 256-bit value; [k]P = [k mod r]P in the r-torsion)
+    static B200_HD int scalar_bit(const uint32_t* k, int i) { return (k[i >> 5] >> (i & 31)) & 1; }
+
+    static B200_HD void scalar_mul(Pt& acc, const Aff& base, const uint32_t* k) {
+        set_inf(acc);
+        for (int i = 255; i >= 0; i--) {
+            dbl(acc);
+            if (scalar_bit(k, i)) madd(acc, base);
+        }
+    }
+    // [e]P + [f]Q, Strauss-Shamir with a joint 1-bit window
+    static B200_HD void scalar_mul2(Pt& acc, const Aff& P, const uint32_t* e, const Aff& Q, const uint32_t* f) {
+        Pt pq;
+        from_affine(pq, P);
+        madd(pq, Q);
+        set_inf(acc);
+        for (int i = 255; i >= 0; i--) {
+            dbl(acc);
+            int b = scalar_bit(e, i) | (scalar_bit(f, i) << 1);
+            if (b == 1) madd(acc, P);
+            else if (b == 2) madd(acc, Q);
+            else if (b == 3) add(acc, pq);
+        }
+    }
+};
+
+}  // namespace b200

@@ -1,0 +1,6 @@
+// BLS377 instantiation of the batch kernels (see kernels.cuh / msm.cuh / launch.cuh).
+#define B200_INSTANTIATE 1
+#include "launch.cuh"
+namespace b200 {
+const CurveVTable* vtable_bls377() { return Launch<BLS377>::table(); }
+}  // namespace b200

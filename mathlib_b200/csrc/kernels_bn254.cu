@@ -1,0 +1,6 @@
+// BN254 instantiation of the batch kernels (see kernels.cuh / msm.cuh / launch.cuh).
+#define B200_INSTANTIATE 1
+#include "launch.cuh"
+namespace b200 {
+const CurveVTable* vtable_bn254() { return Launch<BN254>::table(); }
+}  // namespace b200

@@ -1,0 +1,135 @@
+// Host-side launch wrappers, instantiated once per curve (kernels_<curve>.cu) and reached through a
+// small table of function pointers from the C ABI (abi.cu).  No CPU compute path exists here: every
+// entry launches sm_100a kernels on the given stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include "msm.cuh"
+
+namespace b200 {
+
+extern std::atomic<uint64_t> g_launch_count;
+
+struct MsmBuffers {            // device pointers carved out of one workspace slab by the ABI layer
+    void* points;              // n * sizeof(G1Affine)   (unused when points are already resident)
+    uint32_t* digits;          // W * n
+    uint32_t* sorted;          // W * n
+    uint32_t* counts;          // W * B
+    uint32_t* offsets;         // W * B
+    uint32_t* cursor;          // W * B
+    void* buckets;             // W * B * sizeof(G1XYZZ)
+    void* chunks;              // W * nchunks * sizeof(G1XYZZ)
+    void* windows;             // W * sizeof(G1XYZZ)
+};
+
+struct CurveVTable {
+    int fp_bytes;
+    int limbs;
+    int scalar_bits;
+    size_t aff_size;           // sizeof(G1Affine<N>)
+    size_t xyzz_size;          // sizeof(G1XYZZ<N>)
+    cudaError_t (*pairing)(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
+                           const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
+    cudaError_t (*fexp)(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
+    cudaError_t (*g1_mul)(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
+                          cudaStream_t s);
+    cudaError_t (*g1_mul2)(size_t n, const uint8_t* P, const uint8_t* e, const uint8_t* Q, const uint8_t* f,
+                           uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
+    cudaError_t (*g1_sum)(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
+    // points -> Montgomery affine array (for MSM / resident bases)
+    cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
+    // MSM over prepared points
+    cudaError_t (*msm)(size_t n, const void* prepared_pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
+                       const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s);
+};
+
+const CurveVTable* vtable_bn254();
+const CurveVTable* vtable_bls381();
+const CurveVTable* vtable_bls377();
+
+#if defined(B200_INSTANTIATE)
+static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+#define B200_COUNT_LAUNCH() g_launch_count.fetch_add(1, std::memory_order_relaxed)
+
+template <class C>
+struct Launch {
+    static cudaError_t pairing(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
+                               const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        unsigned nb = blocks_for(n, B200_PAIR_THREADS);
+        if (np == 1) pairing_kernel<C, 1><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err);
+        else pairing_kernel<C, 2><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t fexp(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        fexp_kernel<C><<<blocks_for(n, B200_PAIR_THREADS), B200_PAIR_THREADS, 0, s>>>(n, in, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t g1_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
+                              cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        g1_mul_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, 0, s>>>(n, pts, k, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t g1_mul2(size_t n, const uint8_t* P, const uint8_t* e, const uint8_t* Q, const uint8_t* f,
+                               uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        g1_mul2_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, 0, s>>>(n, P, e, Q, f, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t g1_sum(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
+        g1_sum_kernel<C><<<1, 32, 0, s>>>(n, pts, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t msm_points(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        msm_points_kernel<C><<<blocks_for(n, 128), 128, 0, s>>>(n, pts, (G1Affine<C::N>*)out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t msm(size_t n, const void* pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
+                           const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s) {
+        typedef G1XYZZ<C::N> Pt;
+        size_t nb = (size_t)pl.W * pl.B;
+        cudaError_t e;
+        if ((e = cudaMemsetAsync(b.counts, 0, nb * sizeof(uint32_t), s)) != cudaSuccess) return e;
+        if (n) {
+            msm_digits_kernel<C><<<blocks_for(n, 256), 256, 0, s>>>(n, scalars, pl, b.digits, b.counts);
+            B200_COUNT_LAUNCH();
+        }
+        int st = pl.B >= 1024 ? 1024 : (pl.B >= 32 ? pl.B : 32);
+        msm_scan_kernel<<<pl.W, st, st * sizeof(uint32_t), s>>>(pl, b.counts, b.offsets);
+        B200_COUNT_LAUNCH();
+        if ((e = cudaMemcpyAsync(b.cursor, b.offsets, nb * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s)) != cudaSuccess)
+            return e;
+        if (n) {
+            msm_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, pl, b.digits, b.cursor, b.sorted);
+            B200_COUNT_LAUNCH();
+        }
+        msm_accumulate_kernel<C><<<blocks_for(nb, 128), 128, 0, s>>>(n, pl, (const G1Affine<C::N>*)pts, b.offsets,
+                                                                    b.counts, b.sorted, (Pt*)b.buckets);
+        B200_COUNT_LAUNCH();
+        msm_reduce_kernel<C><<<blocks_for((size_t)pl.W * pl.nchunks, 128), 128, 0, s>>>(pl, (const Pt*)b.buckets,
+                                                                                        (Pt*)b.chunks);
+        B200_COUNT_LAUNCH();
+        msm_window_sum_kernel<C><<<pl.W, 64, 64 * sizeof(Pt), s>>>(pl, (const Pt*)b.chunks, (Pt*)b.windows);
+        B200_COUNT_LAUNCH();
+        msm_final_kernel<C><<<1, 32, 0, s>>>(pl, (const Pt*)b.windows, out, flags);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static const CurveVTable* table() {
+        static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
+                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &msm_points, &msm};
+        return &t;
+    }
+};
+#endif
+
+}  // namespace b200

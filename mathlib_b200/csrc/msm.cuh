@@ -1,0 +1,228 @@
+// Pippenger G1 multi-scalar multiplication (driver.Curve.MultiScalarMul, reference driver/math.go:170;
+// gnark MultiExp call sites bn254.go:232-245, bls12-377.go:229-242, bls12381/bls12-381.go:766-783).
+//
+// Pipeline (all on device, one stream):
+//   1 msm_points_kernel   BYTES -> Montgomery affine points (skipped for MONT input / resident bases)
+//   2 msm_digits_kernel   scalar -> (mod r) -> W signed c-bit digits; per-(window,bucket) histogram
+//   3 msm_scan_kernel     exclusive scan of the histogram per window
+//   4 msm_scatter_kernel  counting-sort point indices by (window, bucket)
+//   5 msm_accumulate_kernel  one thread per bucket: XYZZ mixed adds over its sorted run (coalesced index
+//                            reads, 2*FpBytes gather per point out of L2/HBM)
+//   6 msm_reduce_kernel   sum_b b*B_b per window: chunked running sums, each chunk scaled by its base index
+//   7 msm_window_sum_kernel  per window: tree-sum of the chunk results in shared memory
+//   8 msm_final_kernel    Horner over the windows (c doublings each), affine normalisation, store
+// The result is a canonical group element, so the order of additions inside a bucket does not matter.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200 {
+
+struct MsmPlan {
+    int c;          // window bits
+    int W;          // windows
+    int B;          // buckets per window = 2^(c-1)
+    int chunk;      // buckets per reduce thread
+    int nchunks;    // B / chunk
+};
+
+static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c = lg - 3;
+    if (c < 2) c = 2;
+    if (c > 16) c = 16;
+    MsmPlan p;
+    p.c = c;
+    p.W = scalar_bits / c + 1;
+    p.B = 1 << (c - 1);
+    p.chunk = p.B >= 1024 ? 32 : (p.B >= 32 ? 8 : 1);
+    p.nchunks = p.B / p.chunk;
+    return p;
+}
+
+#if defined(__CUDACC__)
+
+template <class C>
+__global__ void msm_points_kernel(size_t n, const uint8_t* pts, G1Affine<C::N>* out, uint32_t flags, int* err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int e = 0;
+    G1Affine<C::N> a;
+    Codec<C>::g1_load(a.x, a.y, pts + i * Codec<C>::g1_size(), flags & FLAG_IN_MONT, &e);
+    if (e) atomicExch(err, 1);
+    out[i] = a;
+}
+
+// k (8 LE words) mod r by repeated conditional subtraction (k < 2^256 < 14 r for all three curves)
+template <class C>
+__device__ __forceinline__ void scalar_reduce(uint32_t* k) {
+    const uint32_t* r = C::K().order;
+    for (int it = 0; it < 16; it++) {
+        uint32_t t[8];
+        t[0] = sub_cc(k[0], r[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) t[i] = subc_cc(k[i], r[i]);
+        uint32_t borrow = subc(0, 0);
+        if (borrow) break;
+#pragma unroll
+        for (int i = 0; i < 8; i++) k[i] = t[i];
+    }
+}
+
+// digits[w*n + i] = signed digit of scalar i in window w, packed as (|d| << 1) | sign ; 0 = skip
+template <class C>
+__global__ void msm_digits_kernel(size_t n, const uint8_t* scalars, MsmPlan pl, uint32_t* digits, uint32_t* counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[9];
+    Codec<C>::scalar_load(k, scalars + i * 32);
+    scalar_reduce<C>(k);
+    k[8] = 0;
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << pl.c) - 1;
+    for (int w = 0; w < pl.W; w++) {
+        int bit = w * pl.c;
+        uint32_t lo = k[bit >> 5] >> (bit & 31);
+        if ((bit & 31) + pl.c > 32 && (bit >> 5) + 1 < 9) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
+        uint32_t d = (bit < 256 ? (lo & mask) : 0) + carry;
+        uint32_t neg = 0;
+        if (d > (uint32_t)pl.B) { d = (1u << pl.c) - d; neg = 1; carry = 1; } else carry = 0;
+        uint32_t packed = d ? ((d << 1) | neg) : 0;
+        digits[(size_t)w * n + i] = packed;
+        if (d) atomicAdd(&counts[(size_t)w * pl.B + (d - 1)], 1u);
+    }
+}
+
+// per window exclusive scan of counts[w*B .. w*B+B) -> offsets (relative to the window), one block per window
+static __global__ void msm_scan_kernel(MsmPlan pl, const uint32_t* counts, uint32_t* offsets) {
+    extern __shared__ uint32_t sh[];
+    int w = blockIdx.x;
+    const uint32_t* c = counts + (size_t)w * pl.B;
+    uint32_t* o = offsets + (size_t)w * pl.B;
+    int per = (pl.B + blockDim.x - 1) / blockDim.x;
+    int lo = threadIdx.x * per, hi = min(lo + per, pl.B);
+    uint32_t s = 0;
+    for (int j = lo; j < hi; j++) s += c[j];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    // simple Hillis-Steele inclusive scan over blockDim.x partial sums
+    for (int d = 1; d < blockDim.x; d <<= 1) {
+        uint32_t v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t base = sh[threadIdx.x] - s;
+    for (int j = lo; j < hi; j++) { o[j] = base; base += c[j]; }
+}
+
+// sorted[w*n + offsets[w,b] + slot] = (i << 1) | sign ; cursor starts as a copy of offsets
+static __global__ void msm_scatter_kernel(size_t n, MsmPlan pl, const uint32_t* digits, uint32_t* cursor, uint32_t* sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < pl.W; w++) {
+        uint32_t p = digits[(size_t)w * n + i];
+        if (!p) continue;
+        uint32_t b = (p >> 1) - 1;
+        uint32_t pos = atomicAdd(&cursor[(size_t)w * pl.B + b], 1u);
+        sorted[(size_t)w * n + pos] = ((uint32_t)i << 1) | (p & 1);
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(128)
+msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
+                      const uint32_t* sorted, G1XYZZ<C::N>* buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)pl.W * pl.B) return;
+    typedef G1Ops<C> G;
+    size_t w = t / pl.B;
+    const uint32_t* run = sorted + w * n + offsets[t];
+    uint32_t cnt = counts[t];
+    typename G::Pt acc;
+    G::set_inf(acc);
+    for (uint32_t j = 0; j < cnt; j++) {
+        uint32_t e = run[j];
+        typename G::Aff a = pts[e >> 1];
+        if (e & 1) FpOps<C>::neg(a.y, a.y);
+        G::madd(acc, a);
+    }
+    buckets[t] = acc;
+}
+
+// thread (w, chunk t): G = sum_{j=1..S} (t*S + j) * B[w][t*S + j - 1]
+template <class C>
+__global__ void __launch_bounds__(128)
+msm_reduce_kernel(MsmPlan pl, const G1XYZZ<C::N>* buckets, G1XYZZ<C::N>* chunk_out) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (size_t)pl.W * pl.nchunks) return;
+    typedef G1Ops<C> G;
+    size_t w = id / pl.nchunks, t = id % pl.nchunks;
+    const G1XYZZ<C::N>* b = buckets + w * pl.B + t * pl.chunk;
+    typename G::Pt run, acc;
+    G::set_inf(run);
+    G::set_inf(acc);
+    for (int j = pl.chunk - 1; j >= 0; j--) {
+        typename G::Pt v = b[j];
+        G::add(run, v);
+        G::add(acc, run);
+    }
+    // acc = sum (j+1) B_j ; run = sum B_j ; add (t*S) * run
+    uint32_t m = (uint32_t)(t * pl.chunk);
+    if (m) {
+        typename G::Pt s;
+        G::set_inf(s);
+        for (int bit = 31 - __clz(m); bit >= 0; bit--) {
+            G::dbl(s);
+            if ((m >> bit) & 1) G::add(s, run);
+        }
+        G::add(acc, s);
+    }
+    chunk_out[id] = acc;
+}
+
+// one block per window: sum of nchunks chunk results -> window_out[w]
+template <class C>
+__global__ void msm_window_sum_kernel(MsmPlan pl, const G1XYZZ<C::N>* chunk_in, G1XYZZ<C::N>* window_out) {
+    extern __shared__ uint32_t shraw[];
+    typedef G1Ops<C> G;
+    typename G::Pt* sh = reinterpret_cast<typename G::Pt*>(shraw);
+    int w = blockIdx.x;
+    typename G::Pt acc;
+    G::set_inf(acc);
+    for (int j = threadIdx.x; j < pl.nchunks; j += blockDim.x) {
+        typename G::Pt v = chunk_in[(size_t)w * pl.nchunks + j];
+        G::add(acc, v);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = blockDim.x / 2; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            typename G::Pt a = sh[threadIdx.x], b = sh[threadIdx.x + d];
+            G::add(a, b);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) window_out[w] = sh[0];
+}
+
+// Horner over windows, then affine + store. Single thread.
+template <class C>
+__global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_t* out, uint32_t flags) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    typedef G1Ops<C> G;
+    typename G::Pt acc;
+    G::set_inf(acc);
+    for (int w = pl.W - 1; w >= 0; w--) {
+        for (int k = 0; k < pl.c; k++) G::dbl(acc);
+        typename G::Pt v = windows[w];
+        G::add(acc, v);
+    }
+    typename G::Aff r;
+    G::to_affine(r, acc);
+    Codec<C>::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);
+}
+
+#endif  // __CUDACC__
+}  // namespace b200

@@ -65,3 +65,56 @@ extern "C" void he_f12_op(int curve, int op, const uint32_t* a, const uint32_t* 
     else if (curve == 1) t_f12<BLS381>(op, a, b, out);
     else t_f12<BLS377>(op, a, b, out);
 }
+
+#include "../../mathlib_b200/csrc/kernels.cuh"
+// G1 ops through the BYTES codecs (same code path the kernels run per thread)
+template <class C> static int t_g1(int op, const uint8_t* p, const uint8_t* e, const uint8_t* q, const uint8_t* f, uint8_t* out) {
+    typedef Codec<C> CD; typedef G1Ops<C> G;
+    int err = 0;
+    typename G::Aff a, b;
+    CD::g1_load(a.x, a.y, p, false, &err);
+    uint32_t ke[8], kf[8];
+    CD::scalar_load(ke, e);
+    typename G::Pt acc;
+    if (op == 0) {
+        G::scalar_mul(acc, a, ke);
+    } else if (op == 1) {
+        CD::g1_load(b.x, b.y, q, false, &err);
+        CD::scalar_load(kf, f);
+        G::scalar_mul2(acc, a, ke, b, kf);
+    } else {  // sum of two points
+        CD::g1_load(b.x, b.y, q, false, &err);
+        G::from_affine(acc, a);
+        G::madd(acc, b);
+    }
+    G::to_affine(a, acc);
+    CD::g1_store(out, a.x, a.y, false);
+    return err;
+}
+extern "C" int he_g1_op(int curve, int op, const uint8_t* p, const uint8_t* e, const uint8_t* q, const uint8_t* f, uint8_t* out) {
+    if (curve == 0) return t_g1<BN254>(op, p, e, q, f, out);
+    if (curve == 1) return t_g1<BLS381>(op, p, e, q, f, out);
+    return t_g1<BLS377>(op, p, e, q, f, out);
+}
+// pairing through the BYTES codecs
+template <class C> static int t_pair_bytes(int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                                           uint8_t* out, int fexp) {
+    typedef Codec<C> CD; typedef PairingOps<C> PO;
+    constexpr int N = C::N;
+    int err = 0;
+    G1Aff<N> P[2]; G2Aff<N> Q[2];
+    CD::g1_load(P[0].x, P[0].y, g1a, false, &err);
+    CD::g2_load(Q[0], g2a, false, &err);
+    if (np == 2) { CD::g1_load(P[1].x, P[1].y, g1b, false, &err); CD::g2_load(Q[1], g2b, false, &err); }
+    Fp12<N> f;
+    if (np == 1) PO::template miller_loop<1>(f, P, Q); else PO::template miller_loop<2>(f, P, Q);
+    if (fexp) PO::final_exp(f, f);
+    CD::gt_store(out, f, false);
+    return err;
+}
+extern "C" int he_pairing_bytes(int curve, int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                                uint8_t* out, int fexp) {
+    if (curve == 0) return t_pair_bytes<BN254>(np, g1a, g2a, g1b, g2b, out, fexp);
+    if (curve == 1) return t_pair_bytes<BLS381>(np, g1a, g2a, g1b, g2b, out, fexp);
+    return t_pair_bytes<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
+}

@@ -138,8 +138,8 @@ struct Codec {
 // ------------------------------------------------------------------------------------------
 #define B200_PAIR_THREADS 64
 
-template <class C, int NP>
-__global__ void __launch_bounds__(B200_PAIR_THREADS)
+template <class C, int NP, int THREADS = B200_PAIR_THREADS, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
 pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
                uint8_t* out, uint32_t flags, int* err) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

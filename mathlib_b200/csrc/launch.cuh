@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include "msm.cuh"
 
 namespace b200 {
@@ -56,6 +57,20 @@ struct Launch {
     static cudaError_t pairing(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
                                const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
         if (n == 0) return cudaSuccess;
+#if defined(B200_PAIR_VARIANTS)
+        // development switch: occupancy / register-budget variants of the same kernel
+        static int variant = getenv("B200_PAIR_VARIANT") ? atoi(getenv("B200_PAIR_VARIANT")) : 0;
+#define B200_LAUNCH_VARIANT(T, MB)                                                                              \
+        do {                                                                                                    \
+            unsigned nbv = blocks_for(n, T);                                                                    \
+            if (np == 1) pairing_kernel<C, 1, T, MB><<<nbv, T, 0, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err); \
+            else pairing_kernel<C, 2, T, MB><<<nbv, T, 0, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err);         \
+        } while (0)
+        if (variant == 1) { B200_LAUNCH_VARIANT(128, 3); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
+        if (variant == 2) { B200_LAUNCH_VARIANT(128, 4); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
+        if (variant == 3) { B200_LAUNCH_VARIANT(256, 3); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
+        if (variant == 4) { B200_LAUNCH_VARIANT(256, 4); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
+#endif
         unsigned nb = blocks_for(n, B200_PAIR_THREADS);
         if (np == 1) pairing_kernel<C, 1><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err);
         else pairing_kernel<C, 2><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err);

@@ -18,12 +18,15 @@ struct CurveConsts {
     uint32_t frob1[10 * N]; // gamma_{1,i} = xi^(i(p-1)/6),   i=1..5, Fp2 each
     uint32_t frob2[10 * N]; // gamma_{2,i} = xi^(i(p^2-1)/6)
     uint32_t frob3[10 * N]; // gamma_{3,i} = xi^(i(p^3-1)/6)
+    uint32_t p2[31 * 2 * N]; // k * p^2, k = 0..30, 2N words each (lazy-reduction offsets, vm.cuh)
+    uint32_t r3[N];          // R^3 mod p (binary inversion fix-up)
 };
 
 #define B200_DEFINE_CONSTS(NAME, NL)                                                        \
     static const CurveConsts<NL> H_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2, NAME##_B,     \
                                              NAME##_B3, NAME##_BTW, NAME##_ORDER,           \
-                                             NAME##_FROB1, NAME##_FROB2, NAME##_FROB3};
+                                             NAME##_FROB1, NAME##_FROB2, NAME##_FROB3, NAME##_P2, \
+                                             NAME##_R3};
 
 B200_DEFINE_CONSTS(BN254, 8)
 B200_DEFINE_CONSTS(BLS381, 12)
@@ -34,7 +37,8 @@ B200_DEFINE_CONSTS(BLS377, 12)
     static __device__ __constant__ CurveConsts<NL> D_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2,    \
                                                         NAME##_B, NAME##_B3, NAME##_BTW,    \
                                                         NAME##_ORDER, NAME##_FROB1,         \
-                                                        NAME##_FROB2, NAME##_FROB3};
+                                                        NAME##_FROB2, NAME##_FROB3, NAME##_P2,      \
+                                                        NAME##_R3};
 B200_DEFINE_DCONSTS(BN254, 8)
 B200_DEFINE_DCONSTS(BLS381, 12)
 B200_DEFINE_DCONSTS(BLS377, 12)

@@ -5,7 +5,10 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include "msm.cuh"
+#include "pairing_vm.cuh"
 
 namespace b200 {
 
@@ -71,9 +74,57 @@ struct Launch {
         if (variant == 3) { B200_LAUNCH_VARIANT(256, 3); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
         if (variant == 4) { B200_LAUNCH_VARIANT(256, 4); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
 #endif
-        unsigned nb = blocks_for(n, B200_PAIR_THREADS);
-        if (np == 1) pairing_kernel<C, 1><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err);
-        else pairing_kernel<C, 2><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err);
+        static int legacy = getenv("B200_PAIR_LEGACY") ? atoi(getenv("B200_PAIR_LEGACY")) : 0;
+        if (legacy) {   // thread-per-pairing kernel (pairing.cuh), kept as a cross-check of the VM kernel
+            unsigned nb = blocks_for(n, B200_PAIR_THREADS);
+            if (np == 1) pairing_kernel<C, 1><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err);
+            else pairing_kernel<C, 2><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err);
+            B200_COUNT_LAUNCH();
+            return cudaGetLastError();
+        }
+        return vm_pairing(np, n, g1a, g2a, g1b, g2b, out, flags, err, s);
+    }
+    // warp-cooperative VM kernel (pairing_vm.cuh): 6 lanes per pairing product, 40 products per 256-thread block
+    static cudaError_t vm_pairing(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
+                                  const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
+        static thread_local int cfg_dev = -1;
+        static thread_local const uint32_t* d_words = nullptr;
+        static thread_local const VmDirEntry* d_dir = nullptr;
+        cudaError_t e;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        const size_t smem = vm_smem_bytes<C>();
+        if (cfg_dev != dev) {
+            // per device: upload the microcode once and opt in to the large dynamic shared memory carve-out
+            static std::mutex mu;
+            static std::map<int, std::pair<const uint32_t*, const VmDirEntry*>> tables;
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = tables.find(dev);
+            if (it == tables.end()) {
+                uint32_t* w = nullptr;
+                VmDirEntry* d = nullptr;
+                if ((e = cudaMalloc(&w, sizeof(uint32_t) * VmTables<C>::NWORDS)) != cudaSuccess) return e;
+                if ((e = cudaMalloc(&d, sizeof(VmDirEntry) * VP_COUNT)) != cudaSuccess) return e;
+                if ((e = cudaMemcpy(w, VmTables<C>::host_words(), sizeof(uint32_t) * VmTables<C>::NWORDS,
+                                    cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+                if ((e = cudaMemcpy(d, VmTables<C>::host_dir(), sizeof(VmDirEntry) * VP_COUNT, cudaMemcpyHostToDevice)) !=
+                    cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem)) != cudaSuccess) return e;
+                it = tables.emplace(dev, std::make_pair((const uint32_t*)w, (const VmDirEntry*)d)).first;
+            }
+            d_words = it->second.first;
+            d_dir = it->second.second;
+            cfg_dev = dev;
+        }
+        const unsigned gpb = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
+        const unsigned nb = (unsigned)((n + gpb - 1) / gpb);
+        if (np == 1)
+            vm_pairing_kernel<C, 1><<<nb, B200_VM_WARPS * 32, smem, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err, d_words, d_dir);
+        else
+            vm_pairing_kernel<C, 2><<<nb, B200_VM_WARPS * 32, smem, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }

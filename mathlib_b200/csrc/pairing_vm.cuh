@@ -1,0 +1,335 @@
+// Warp-cooperative pairing kernel: 6 lanes per pairing product, state in shared memory, control flow below,
+// arithmetic in the VM interpreter (vm.cuh) running microcode compiled from mathlib_b200/vm/programs.py.
+// The sequence of program runs is the one of mathlib_b200/vm/driver_ref.py (checked against the oracle on the CPU).
+//
+// Same results as pairing.cuh (thread-per-pairing): raw Miller value per SURVEY A.5, canonical value after FExp.
+// Replaces the same reference calls: driver.Curve.Pairing / Pairing2 / FExp (reference driver/math.go:51-57).
+#pragma once
+#include "vm.cuh"
+#include "kernels.cuh"
+
+namespace b200 {
+
+template <class C> struct VmTables;
+#define B200_VM_TABLES(NAME, CURVE)                                                                       \
+    static const uint32_t H_VMW_##NAME[] = VM_##NAME##_WORDS;                                             \
+    static const VmDirEntry H_VMD_##NAME[VP_COUNT] = VM_##NAME##_DIR;                                     \
+    template <> struct VmTables<CURVE> {                                                                  \
+        static constexpr int NSLOTS = VM_##NAME##_NSLOTS;                                                 \
+        static constexpr int NREGS = VM_##NAME##_NREGS;                                                   \
+        static constexpr int NWORDS = VM_##NAME##_NWORDS;                                                 \
+        static const uint32_t* host_words() { return H_VMW_##NAME; }                                      \
+        static const VmDirEntry* host_dir() { return H_VMD_##NAME; }                                      \
+    };
+B200_VM_TABLES(BN254, BN254)
+B200_VM_TABLES(BLS381, BLS381)
+B200_VM_TABLES(BLS377, BLS377)
+
+constexpr int VM_KBANK = 18;      // one, b', zero, 15 Frobenius constants
+
+// constant bank in Montgomery form: [one, btw, zero, frob1[1..5], frob2[1..5], frob3[1..5]]
+template <class C>
+B200_HD void vm_fill_kbank(uint32_t* kb, int idx) {
+    constexpr int N = C::N;
+    const uint32_t* src = nullptr;
+    if (idx == 0) {
+        for (int i = 0; i < N; i++) { kb[i] = C::one()[i]; kb[N + i] = 0; }
+        return;
+    }
+    if (idx == 2) {
+        for (int i = 0; i < 2 * N; i++) kb[i] = 0;
+        return;
+    }
+    if (idx == 1) src = C::K().btw;
+    else {
+        int k = (idx - 3) / 5, i = (idx - 3) % 5;
+        src = (k == 0 ? C::K().frob1 : k == 1 ? C::K().frob2 : C::K().frob3) + i * 2 * N;
+    }
+    for (int i = 0; i < 2 * N; i++) kb[i] = src[i];
+}
+
+template <class C>
+struct VmDriver {
+    static constexpr int N = C::N;
+    static constexpr int SW = 2 * N;
+    typedef Vm<C> M;
+    typedef VmTables<C> TB;
+    typedef Codec<C> CD;
+    typedef FpOps<C> F;
+
+    typename M::Ctx ctx;
+    const uint32_t* words;
+    const VmDirEntry* dir;
+    int role;                 // device: this lane's role (0..5, or -1 idle); host emulation: ignored
+
+    B200_HD void sync() {
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
+    B200_HD_NOINLINE void run(int prog, uint32_t b1, uint32_t b2, uint32_t b3) {
+        ctx.base[0] = b1; ctx.base[1] = b2; ctx.base[2] = b3;
+        const uint32_t* w = words + dir[prog].offset;
+        const uint32_t nph = dir[prog].phases;
+        for (uint32_t ph = 0; ph < nph; ph++) {
+#if defined(__CUDA_ARCH__)
+            if (role >= 0) M::exec_op(ctx, w + (ph * VM_G + role) * VM_OP_WORDS);
+            __syncwarp();
+#else
+            for (int r = 0; r < VM_G; r++) M::exec_op(ctx, w + (ph * VM_G + r) * VM_OP_WORDS);
+#endif
+        }
+    }
+
+    // ---- Miller loop; returns the slot base of f
+    template <int NP>
+    B200_HD uint32_t miller() {
+        uint32_t cur = 0, nxt = 6;
+        run(NP == 1 ? VP_INIT1 : VP_INIT2, cur, nxt, 0);
+        const bool dbl_swaps = ((1 + NP) & 1) != 0, add_swaps = (NP & 1) != 0;
+        const int len = PairingOps<C>::loop_len();
+        int top = len - 1;
+        while (PairingOps<C>::loop_digit(top) == 0) top--;
+        for (int i = top - 1; i >= 0; i--) {
+            run(NP == 1 ? VP_DBL1 : VP_DBL2, cur, nxt, 0);
+            if (dbl_swaps) { uint32_t t = cur; cur = nxt; nxt = t; }
+            int d = PairingOps<C>::loop_digit(i);
+            if (d) {
+                run(NP == 1 ? VP_ADD1 : VP_ADD2, cur, nxt, d > 0 ? 0u : 1u);
+                if (add_swaps) { uint32_t t = cur; cur = nxt; nxt = t; }
+            }
+        }
+        if (C::FAMILY == FAMILY_BN) run(NP == 1 ? VP_BNTAIL1 : VP_BNTAIL2, cur, nxt, 0);
+        if (C::X_NEG) {
+            run(VP_CONJ, nxt, cur, 0);
+            uint32_t t = cur; cur = nxt; nxt = t;
+        }
+        return cur;
+    }
+
+    // ---- final exponentiation over NREGS Fp12 registers; returns the slot base of the result
+    struct Regs {
+        uint32_t freemask;
+        B200_HD int alloc() {
+            int r = 0;
+            while (!((freemask >> r) & 1)) r++;
+            freemask &= ~(1u << r);
+            return r;
+        }
+        B200_HD void release(int r) { freemask |= 1u << r; }
+    };
+    Regs R;
+    B200_HD int op(int prog, int a, int b = 0) {
+        int d = R.alloc();
+        run(prog, 6 * d, 6 * a, 6 * b);
+        return d;
+    }
+    B200_HD int expx(int z) {
+        int top = 63;
+        while (!((C::X_ABS >> top) & 1)) top--;
+        int acc = -1;
+        for (int i = top - 1; i >= 0; i--) {
+            int n = op(VP_CYCLO_SQR, acc < 0 ? z : acc);
+            if (acc >= 0) R.release(acc);
+            acc = n;
+            if ((C::X_ABS >> i) & 1) {
+                n = op(VP_F12_MUL, acc, z);
+                R.release(acc);
+                acc = n;
+            }
+        }
+        if (C::X_NEG) {
+            int n = op(VP_CONJ, acc);
+            R.release(acc);
+            acc = n;
+        }
+        return acc;
+    }
+    B200_HD uint32_t final_exp(uint32_t f_base) {
+        int f = (int)(f_base / 6);
+        R.freemask = ((1u << TB::NREGS) - 1) & ~(1u << f);
+        int x;
+        int ri = op(VP_F12_INV, f);
+        int c = op(VP_CONJ, f);
+        R.release(f);
+        int t = op(VP_F12_MUL, c, ri);
+        R.release(c); R.release(ri);
+        int u = op(VP_FROB2, t);
+        f = op(VP_F12_MUL, u, t);
+        R.release(u); R.release(t);
+        if (C::FAMILY == FAMILY_BLS12) {
+            int t0 = op(VP_CYCLO_SQR, f);
+            int t1 = expx(f);
+            int t2 = op(VP_CONJ, f);
+            x = op(VP_F12_MUL, t1, t2); R.release(t1); R.release(t2); t1 = x;
+            t2 = expx(t1);
+            x = op(VP_CONJ, t1); R.release(t1); t1 = x;
+            x = op(VP_F12_MUL, t1, t2); R.release(t1); R.release(t2); t1 = x;
+            t2 = expx(t1);
+            x = op(VP_FROB1, t1); R.release(t1); t1 = x;
+            x = op(VP_F12_MUL, t1, t2); R.release(t1); R.release(t2); t1 = x;
+            x = op(VP_F12_MUL, f, t0); R.release(f); R.release(t0); f = x;
+            t0 = expx(t1);
+            t2 = expx(t0);
+            R.release(t0);
+            t0 = op(VP_FROB2, t1);
+            x = op(VP_CONJ, t1); R.release(t1); t1 = x;
+            x = op(VP_F12_MUL, t1, t2); R.release(t1); R.release(t2); t1 = x;
+            x = op(VP_F12_MUL, t1, t0); R.release(t1); R.release(t0); t1 = x;
+            x = op(VP_F12_MUL, f, t1); R.release(f); R.release(t1); f = x;
+            return 6u * f;
+        }
+        int e = expx(f);
+        int t0 = op(VP_CONJ, e); R.release(e);
+        x = op(VP_CYCLO_SQR, t0); R.release(t0); t0 = x;
+        int t1 = op(VP_CYCLO_SQR, t0);
+        x = op(VP_F12_MUL, t0, t1); R.release(t1); t1 = x;
+        e = expx(t1);
+        int t2 = op(VP_CONJ, e); R.release(e);
+        int t3 = op(VP_CONJ, t1);
+        x = op(VP_F12_MUL, t2, t3); R.release(t1); R.release(t3); t1 = x;
+        t3 = op(VP_CYCLO_SQR, t2);
+        int t4 = expx(t3);
+        x = op(VP_F12_MUL, t1, t4); R.release(t4); R.release(t1); t4 = x;
+        x = op(VP_F12_MUL, t0, t4); R.release(t3); t3 = x;
+        x = op(VP_F12_MUL, t2, t4); R.release(t0); R.release(t2); t0 = x;
+        x = op(VP_F12_MUL, f, t0); R.release(t0); t0 = x;
+        t2 = op(VP_FROB1, t3);
+        x = op(VP_F12_MUL, t2, t0); R.release(t2); R.release(t0); t0 = x;
+        t2 = op(VP_FROB2, t4); R.release(t4);
+        x = op(VP_F12_MUL, t2, t0); R.release(t2); R.release(t0); t0 = x;
+        t2 = op(VP_CONJ, f); R.release(f);
+        x = op(VP_F12_MUL, t2, t3); R.release(t2); R.release(t3); t2 = x;
+        x = op(VP_FROB3, t2); R.release(t2); t2 = x;
+        x = op(VP_F12_MUL, t2, t0); R.release(t2); R.release(t0); t0 = x;
+        return 6u * t0;
+    }
+
+    // ---- I/O: lane `r` of the group converts coordinate r of pair k (P.x, P.y, Q.x.c0, Q.x.c1, Q.y.c0, Q.y.c1)
+    // returns 1 if the coordinate is zero; *err set on a bad encoding
+    B200_HD int load_coord(int r, int k, const uint8_t* g1, const uint8_t* g2, bool mont, int* err) {
+        Fp<N> v;
+        const int FB = C::FP_BYTES;
+        if (r < 2) {
+            if (mont) CD::fp_from_mont_words(v, (const uint32_t*)g1 + r * N);
+            else {
+                uint8_t fl = g1[0] & CD::flag_mask();
+                if (C::FLAG_BITS == 3 && fl == 0x40) F::zero(v);
+                else if (fl != 0) { *err = 1; F::zero(v); }
+                else CD::fp_from_bytes(v, g1 + r * FB, r == 0 ? (uint8_t)~CD::flag_mask() : 0xFF, err);
+            }
+            uint32_t* dst = ctx.slots + (24 + k) * SW + r * N;
+            for (int i = 0; i < N; i++) dst[i] = v.l[i];
+        } else {
+            int q = r - 2;                    // 0: x.c0, 1: x.c1, 2: y.c0, 3: y.c1
+            if (mont) CD::fp_from_mont_words(v, (const uint32_t*)g2 + q * N);
+            else {
+                uint8_t fl = g2[0] & CD::flag_mask();
+                // wire order X.A1 | X.A0 | Y.A1 | Y.A0
+                int pos = (q ^ 1);
+                if (C::FLAG_BITS == 3 && fl == 0x40) F::zero(v);
+                else if (fl != 0) { *err = 1; F::zero(v); }
+                else CD::fp_from_bytes(v, g2 + pos * FB, pos == 0 ? (uint8_t)~CD::flag_mask() : 0xFF, err);
+            }
+            uint32_t* dst = ctx.slots + (18 + 3 * k + (q >> 1)) * SW + (q & 1) * N;
+            for (int i = 0; i < N; i++) dst[i] = v.l[i];
+        }
+        return F::is_zero(v) ? 1 : 0;
+    }
+    // lane r stores w-basis coefficient r (2 Fp) of the Fp12 at slot base fb
+    B200_HD void store_coeff(int r, uint32_t fb, uint8_t* out, bool mont) {
+        const uint32_t* src = ctx.slots + (fb + r) * SW;
+        for (int a = 0; a < 2; a++) {
+            Fp<N> v;
+            for (int i = 0; i < N; i++) v.l[i] = src[a * N + i];
+            int e = ((r & 1) * 3 + (r >> 1)) * 2 + a;       // index in the C0.B0.A0 ... C1.B2.A1 order
+            if (mont) CD::fp_to_mont_words((uint32_t*)out + e * N, v);
+            else CD::fp_to_bytes(out + (11 - e) * C::FP_BYTES, v);
+        }
+    }
+    B200_HD bool coeff_is_one_part(int r, uint32_t fb) {
+        const uint32_t* src = ctx.slots + (fb + r) * SW;
+        uint32_t d = 0;
+        for (int i = 0; i < N; i++) {
+            d |= src[i] ^ (r == 0 ? C::one()[i] : 0u);
+            d |= src[N + i];
+        }
+        return d == 0;
+    }
+};
+
+#if defined(__CUDACC__)
+#define B200_VM_WARPS 8
+#define B200_VM_GROUPS_PER_WARP 5
+#define B200_VM_GROUP_PAD 4          // words; staggers the groups across shared-memory banks
+
+template <class C>
+__host__ __device__ constexpr size_t vm_group_stride() { return (size_t)VmTables<C>::NSLOTS * 2 * C::N + B200_VM_GROUP_PAD; }
+template <class C>
+__host__ __device__ constexpr size_t vm_smem_bytes() {
+    return 4 * ((size_t)B200_VM_WARPS * B200_VM_GROUPS_PER_WARP * vm_group_stride<C>() + (size_t)VM_KBANK * 2 * C::N +
+                (size_t)VmTables<C>::NWORDS + VP_COUNT * 2);
+}
+
+template <class C, int NP>
+__global__ void __launch_bounds__(B200_VM_WARPS * 32, 1)
+vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                  uint8_t* out, uint32_t flags, int* err, const uint32_t* mc_words, const VmDirEntry* mc_dir) {
+    extern __shared__ uint32_t smem[];
+    constexpr int N = C::N;
+    constexpr int GPB = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
+    uint32_t* s_slots = smem;
+    uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
+    uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
+    if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = lane / VM_G;                          // group within warp (5 = idle lanes 30, 31)
+    const int role = gw < B200_VM_GROUPS_PER_WARP ? lane % VM_G : -1;
+    const int gblock = warp * B200_VM_GROUPS_PER_WARP + (gw < B200_VM_GROUPS_PER_WARP ? gw : 0);
+    const size_t item = (size_t)blockIdx.x * GPB + gblock;
+    const bool active = role >= 0 && item < n;
+
+    VmDriver<C> D;
+    D.ctx.slots = s_slots + (size_t)gblock * vm_group_stride<C>();
+    D.ctx.kbank = s_kbank;
+    D.words = s_words;
+    D.dir = s_dir;
+    D.role = active ? role : -1;
+    typedef Codec<C> CD;
+    const bool in_mont = flags & FLAG_IN_MONT;
+    int e = 0, z0 = 0, z1 = 0;
+    if (active) {
+        z0 = D.load_coord(role, 0, g1a + item * CD::g1_size(), g2a + item * CD::g2_size(), in_mont, &e);
+        if (NP == 2) z1 = D.load_coord(role, 1, g1b + item * CD::g1_size(), g2b + item * CD::g2_size(), in_mont, &e);
+    }
+    // group-wide view of the zero flags: pair k is dead if P (roles 0,1) or Q (roles 2..5) is all zero
+    const unsigned b0 = __ballot_sync(0xffffffffu, z0 != 0), b1 = __ballot_sync(0xffffffffu, z1 != 0);
+    const unsigned any_err = __ballot_sync(0xffffffffu, e != 0);
+    if (any_err) {
+        if (lane == 0) atomicExch(err, 1);
+        return;
+    }
+    const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+    const unsigned m0 = (b0 >> sh) & 63u, m1 = (b1 >> sh) & 63u;
+    const bool dead0 = ((m0 & 3u) == 3u) || ((m0 & 60u) == 60u);
+    const bool dead1 = NP == 2 ? (((m1 & 3u) == 3u) || ((m1 & 60u) == 60u)) : true;
+    D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
+    __syncwarp();
+    uint32_t fb = D.template miller<NP>();
+    if (flags & FLAG_FEXP) fb = D.final_exp(fb);
+    if (flags & FLAG_UNITY) {
+        const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
+    } else if (active) {
+        D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+    }
+}
+#endif
+
+}  // namespace b200

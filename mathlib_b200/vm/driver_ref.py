@@ -1,0 +1,174 @@
+"""Reference control flow of the VM pairing kernel in Python (executes the compiled microcode with compiler.simulate).
+
+csrc/pairing_vm.cuh follows exactly this sequence of program runs; the tests run it against the oracle, so a
+microcode or sequencing bug is caught on the CPU.  Values here are canonical residues (the CUDA side holds the same
+values in Montgomery form).
+"""
+from . import programs as PR
+from .compiler import Field, simulate
+
+
+class CurveCtx:
+    def __init__(self, name, p, beta, xi, x_abs, x_neg, naf, btw, frob):
+        self.name = name
+        self.F = Field(p, beta, xi)
+        self.p = p
+        self.x_abs, self.x_neg, self.naf = x_abs, x_neg, naf
+        self.cv = PR.CURVES[name]
+        self.progs = PR.build_all(name)
+        self.nslots, self.nregs = PR.SLOTCFG[name]
+        # constant bank: one, b', zero, then frobenius gamma_{k,i}
+        self.consts = [(1, 0), btw, (0, 0)] + [frob[k][i] for k in (1, 2, 3) for i in range(1, 6)]
+
+    def run(self, name, slots, bases=(0, 0, 0), live=(True, True)):
+        simulate(self.F, self.progs[name].words, slots, self.consts, bases, live)
+
+
+def loop_digits(ctx):
+    if ctx.cv.family == 'bls12':
+        return [(ctx.x_abs >> i) & 1 for i in range(64)]
+    return ctx.naf
+
+
+def miller(ctx, pairs):
+    """pairs: list of (P=(x,y)|None, Q=((x0,x1),(y0,y1))|None), 1 or 2 entries. Returns (slots, f_base)."""
+    np_ = len(pairs)
+    slots = [(0, 0)] * ctx.nslots
+    live = [True, True]
+    for k, (P, Q) in enumerate(pairs):
+        live[k] = P is not None and Q is not None
+        P = P or (0, 0)
+        Q = Q or ((0, 0), (0, 0))
+        slots[PR.Q_BASE + 3 * k] = Q[0]
+        slots[PR.Q_BASE + 3 * k + 1] = Q[1]
+        slots[PR.P_BASE + k] = (P[0], P[1])
+    cur, nxt = 0, 6
+    ctx.run('INIT%d' % np_, slots, (cur, nxt, 0), live)
+    digits = loop_digits(ctx)
+    top = len(digits) - 1
+    while digits[top] == 0:
+        top -= 1
+    dbl_swaps = (1 + np_) % 2 == 1
+    add_swaps = np_ % 2 == 1
+    for i in range(top - 1, -1, -1):
+        ctx.run('DBL%d' % np_, slots, (cur, nxt, 0), live)
+        if dbl_swaps:
+            cur, nxt = nxt, cur
+        d = digits[i]
+        if d:
+            ctx.run('ADD%d' % np_, slots, (cur, nxt, 0 if d > 0 else 1), live)
+            if add_swaps:
+                cur, nxt = nxt, cur
+    if ctx.cv.family == 'bn':
+        ctx.run('BNTAIL%d' % np_, slots, (cur, nxt, 0), live)
+        # 2*np_ rewrites: even -> no swap
+    if ctx.x_neg:
+        ctx.run('CONJ', slots, (nxt, cur, 0), live)
+        cur, nxt = nxt, cur
+    return slots, cur
+
+
+class Regs:
+    def __init__(self, n, used):
+        self.free = [r for r in range(n) if r not in used]
+
+    def alloc(self):
+        return self.free.pop(0)
+
+    def release(self, *rs):
+        for r in rs:
+            self.free.append(r)
+        self.free.sort()
+
+
+def final_exp(ctx, slots, f_base):
+    """slots: register file with f at f_base (0 or 6). Returns base of the result."""
+    R = Regs(ctx.nregs, [f_base // 6])
+
+    def op(name, a, b=None):
+        d = R.alloc()
+        ctx.run(name, slots, (6 * d, 6 * a, 6 * (b if b is not None else 0)))
+        return d
+
+    def expx(z):
+        """returns register holding z^x; z is kept"""
+        top = 63
+        while not (ctx.x_abs >> top) & 1:
+            top -= 1
+        acc = None
+        for i in range(top - 1, -1, -1):
+            n = op('CYCLO_SQR', z if acc is None else acc)
+            if acc is not None:
+                R.release(acc)
+            acc = n
+            if (ctx.x_abs >> i) & 1:
+                n = op('F12_MUL', acc, z)
+                R.release(acc)
+                acc = n
+        if ctx.x_neg:
+            n = op('CONJ', acc)
+            R.release(acc)
+            acc = n
+        return acc
+
+    f = f_base // 6
+    ri = op('F12_INV', f)
+    c = op('CONJ', f)
+    R.release(f)
+    t = op('F12_MUL', c, ri)
+    R.release(c, ri)
+    u = op('FROB2', t)
+    f = op('F12_MUL', u, t)
+    R.release(u, t)
+    if ctx.cv.family == 'bls12':
+        t0 = op('CYCLO_SQR', f)
+        t1 = expx(f)
+        t2 = op('CONJ', f)
+        x = op('F12_MUL', t1, t2); R.release(t1, t2); t1 = x
+        t2 = expx(t1)
+        x = op('CONJ', t1); R.release(t1); t1 = x
+        x = op('F12_MUL', t1, t2); R.release(t1, t2); t1 = x
+        t2 = expx(t1)
+        x = op('FROB1', t1); R.release(t1); t1 = x
+        x = op('F12_MUL', t1, t2); R.release(t1, t2); t1 = x
+        x = op('F12_MUL', f, t0); R.release(f, t0); f = x
+        t0 = expx(t1)
+        t2 = expx(t0)
+        R.release(t0)
+        t0 = op('FROB2', t1)
+        x = op('CONJ', t1); R.release(t1); t1 = x
+        x = op('F12_MUL', t1, t2); R.release(t1, t2); t1 = x
+        x = op('F12_MUL', t1, t0); R.release(t1, t0); t1 = x
+        x = op('F12_MUL', f, t1); R.release(f, t1); f = x
+        return 6 * f
+    # BN254: Fuentes-Castaneda chain
+    e = expx(f)
+    t0 = op('CONJ', e); R.release(e)
+    x = op('CYCLO_SQR', t0); R.release(t0); t0 = x
+    t1 = op('CYCLO_SQR', t0)
+    x = op('F12_MUL', t0, t1); R.release(t1); t1 = x
+    e = expx(t1)
+    t2 = op('CONJ', e); R.release(e)
+    t3 = op('CONJ', t1)
+    x = op('F12_MUL', t2, t3); R.release(t1, t3); t1 = x
+    t3 = op('CYCLO_SQR', t2)
+    t4 = expx(t3)
+    x = op('F12_MUL', t1, t4); R.release(t4, t1); t4 = x
+    x = op('F12_MUL', t0, t4); R.release(t3); t3 = x
+    x = op('F12_MUL', t2, t4); R.release(t0, t2); t0 = x
+    x = op('F12_MUL', f, t0); R.release(t0); t0 = x
+    t2 = op('FROB1', t3)
+    x = op('F12_MUL', t2, t0); R.release(t2, t0); t0 = x
+    t2 = op('FROB2', t4); R.release(t4)
+    x = op('F12_MUL', t2, t0); R.release(t2, t0); t0 = x
+    t2 = op('CONJ', f); R.release(f)
+    x = op('F12_MUL', t2, t3); R.release(t2, t3); t2 = x
+    x = op('FROB3', t2); R.release(t2); t2 = x
+    x = op('F12_MUL', t2, t0); R.release(t2, t0); t0 = x
+    return 6 * t0
+
+
+def f12_from_slots(slots, base):
+    """w-basis g0..g5 -> ((C0.B0,C0.B1,C0.B2),(C1.B0,C1.B1,C1.B2))"""
+    g = slots[base:base + 6]
+    return ((g[0], g[2], g[4]), (g[1], g[3], g[5]))

@@ -1,0 +1,336 @@
+"""Straight-line Fp2-level programs of the pairing VM, written against compiler.py's DSL.
+
+Fp12 elements are held in the w-basis: g_k (k = 0..5) is the Fp2 coefficient of w^k, w^6 = xi, i.e.
+g0..g5 = C0.B0, C1.B0, C0.B1, C1.B1, C0.B2, C1.B2 of the gnark/kilic E12 layout.
+
+Slot maps
+  Miller loop: F double buffer at base registers B1 (current) / B2 (next), 6 slots each (absolute 0..5 / 6..11);
+               pair k: T = (X,Y,Z) at 12+3k, Q = (x, y, -y) at 18+3k (y is addressed through B3 = 0 / 1 to pick y / -y
+               for the signed NAF digits of BN254), P at 24+k (c0 = xP, c1 = yP); temporaries 26..47.
+  Final exp.:  NREGS Fp12 registers at 0,6,12,...; temporaries after them; programs take (B1,B2,B3) = (dst, a, b) bases.
+The formulas are the ones of csrc/pairing.cuh (SURVEY A.5 doubling / addition steps, sparse line slots, Granger-Scott
+squaring); tests/test_vm_programs.py checks every compiled program against the oracle.
+"""
+from .compiler import (ref, const, dot, lin, inv, mul, sqr, compile_program, NEG, CONJ, XI, DBL, REAL0, REAL1,
+                       C_ABS, C_B1, C_B2, C_B3, C_CONST)
+
+T_BASE, Q_BASE, P_BASE = 12, 18, 24
+MILLER_TEMP0 = 26
+# per-curve slot file: BLS12 curves (96-byte slots): 48 slots, 5 Fp12 registers for the final exponentiation;
+# BN254 (64-byte slots): 72 slots, 8 registers (the Fuentes-Castaneda chain keeps more values alive).  Both are 4,608 B.
+SLOTCFG = {'BLS381': (48, 5), 'BLS377': (48, 5), 'BN254': (72, 8)}
+_cfg = {'nslots': 48, 'nregs': 5}
+
+
+def miller_temps():
+    return list(range(MILLER_TEMP0, _cfg['nslots']))
+
+
+def fexp_temps():
+    return list(range(6 * _cfg['nregs'], _cfg['nslots']))
+
+# constant bank indices
+K_ONE, K_BTW, K_ZERO = 0, 1, 2
+K_FROB = 3          # K_FROB + 5*(k-1) + (i-1), k = 1..3, i = 1..5
+
+
+def k_frob(k, i):
+    return K_FROB + 5 * (k - 1) + (i - 1)
+
+
+class Curve:
+    def __init__(self, name, twist, family, btw_is_4xi):
+        self.name, self.twist, self.family, self.btw_is_4xi = name, twist, family, btw_is_4xi
+        self.supp = (0, 2, 3) if twist == 'M' else (0, 1, 3)     # powers of w carrying the line coefficients
+
+
+CURVES = {
+    'BN254': Curve('BN254', 'D', 'bn', False),
+    'BLS381': Curve('BLS381', 'M', 'bls12', True),
+    'BLS377': Curve('BLS377', 'D', 'bls12', False),
+}
+
+
+# ------------------------------------------------------------------------------------------------ Fp12 building blocks
+def f12_mul_nodes(a, b):
+    out = []
+    for k in range(6):
+        terms = []
+        for i in range(6):
+            j = (k - i) % 6
+            am = XI if i + j >= 6 else 0
+            terms.append(((a[i], am), b[j]))
+        out.append(dot(terms, name='m%d' % k))
+    return out
+
+
+def f12_sqr_nodes(a):
+    out = []
+    for k in range(6):
+        terms = []
+        for i in range(6):
+            j = (k - i) % 6
+            if i > j:
+                continue
+            am = (XI if i + j >= 6 else 0) | (DBL if i != j else 0)
+            terms.append(((a[i], am), a[j]))
+        out.append(dot(terms, name='s%d' % k))
+    return out
+
+
+def sparse_mul_nodes(a, line, supp, pred, alt):
+    """a * (sum_s line[s] w^s); line: dict power -> Val"""
+    out = []
+    for k in range(6):
+        terms = []
+        for s in supp:
+            i = (k - s) % 6
+            am = XI if k - s < 0 else 0
+            terms.append(((a[i], am), line[s]))
+        out.append(dot(terms, pred=pred, alt=alt[k], name='sp%d' % k))
+    return out
+
+
+def cyclo_sqr_nodes(g):
+    """Granger-Scott; Fp4 pairs (g0,g3), (g1,g4), (g2,g5)."""
+    o = [None] * 6
+    # g0' = 3(g0^2 + xi g3^2) - 2 g0 ; g3' = 3*(2 g0 g3) + 2 g3
+    o[0] = dot([(g[0], g[0]), ((g[3], XI), g[3])], scale=3, lin=[(g[0], -2)])
+    o[3] = dot([((g[0], DBL), g[3])], scale=3, lin=[(g[3], 2)])
+    # g1' = 3 xi (2 g2 g5) + 2 g1 ; g4' = 3(g2^2 + xi g5^2) - 2 g4
+    o[1] = dot([((g[2], XI | DBL), g[5])], scale=3, lin=[(g[1], 2)])
+    o[4] = dot([(g[2], g[2]), ((g[5], XI), g[5])], scale=3, lin=[(g[4], -2)])
+    # g2' = 3(g1^2 + xi g4^2) - 2 g2 ; g5' = 3*(2 g1 g4) + 2 g5
+    o[2] = dot([(g[1], g[1]), ((g[4], XI), g[4])], scale=3, lin=[(g[2], -2)])
+    o[5] = dot([((g[1], DBL), g[4])], scale=3, lin=[(g[5], 2)])
+    return o
+
+
+def f12_inv_nodes(g):
+    x = [g[0], g[2], g[4]]          # C0 = x0 + x1 v + x2 v^2
+    y = [g[1], g[3], g[5]]          # C1
+    # d = C0^2 - v C1^2
+    d0 = dot([(x[0], x[0]), ((x[1], XI | DBL), x[2]), ((y[0], XI | DBL | NEG), y[2]), ((y[1], XI | NEG), y[1])])
+    d1 = dot([((x[0], DBL), x[1]), ((x[2], XI), x[2]), ((y[0], NEG), y[0]), ((y[1], XI | DBL | NEG), y[2])])
+    d2 = dot([((x[0], DBL), x[2]), (x[1], x[1]), ((y[0], DBL | NEG), y[1]), ((y[2], XI | NEG), y[2])])
+    t0 = dot([(d0, d0), ((d1, XI | NEG), d2)])
+    t1 = dot([((d2, XI), d2), ((d0, NEG), d1)])
+    t2 = dot([(d1, d1), ((d0, NEG), d2)])
+    n = dot([(d0, t0), ((d2, XI), t1), ((d1, XI), t2)])
+    ni = inv(n)
+    e = [mul(t0, ni), mul(t1, ni), mul(t2, ni)]
+
+    def f6mul(u, v, neg):
+        m = NEG if neg else 0
+        z0 = dot([((u[0], m), v[0]), ((u[1], XI | m), v[2]), ((u[2], XI | m), v[1])])
+        z1 = dot([((u[0], m), v[1]), ((u[1], m), v[0]), ((u[2], XI | m), v[2])])
+        z2 = dot([((u[0], m), v[2]), ((u[1], m), v[1]), ((u[2], m), v[0])])
+        return [z0, z1, z2]
+    c0 = f6mul(x, e, False)
+    c1 = f6mul(y, e, True)
+    return [c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]]
+
+
+def regs(cls, base=0):
+    return [ref(cls, base + k) for k in range(6)]
+
+
+def bind(nodes, cls, base=0):
+    return [(n, (cls, base + k)) for k, n in enumerate(nodes)]
+
+
+# ------------------------------------------------------------------------------------------------ final-exp programs
+def prog_f12_mul():
+    return compile_program('F12_MUL', bind(f12_mul_nodes(regs(C_B2), regs(C_B3)), C_B1), fexp_temps())
+
+
+def prog_cyclo():
+    return compile_program('CYCLO_SQR', bind(cyclo_sqr_nodes(regs(C_B2)), C_B1), fexp_temps())
+
+
+def prog_conj():
+    a = regs(C_B2)
+    return compile_program('CONJ', bind([lin([((a[k], NEG if k & 1 else 0), 1)]) for k in range(6)], C_B1), fexp_temps())
+
+
+def prog_frob(k):
+    a = regs(C_B2)
+    cm = CONJ if k & 1 else 0
+    nodes = [lin([((a[0], cm), 1)])]
+    for i in range(1, 6):
+        nodes.append(dot([((a[i], cm), const(k_frob(k, i)))]))
+    return compile_program('FROB%d' % k, bind(nodes, C_B1), fexp_temps())
+
+
+def prog_inv():
+    return compile_program('F12_INV', bind(f12_inv_nodes(regs(C_B2)), C_B1), fexp_temps())
+
+
+# ------------------------------------------------------------------------------------------------ Miller-loop programs
+def _line_and_sparse(cv, f_cur, lines_per_pair, f_slots_cycle):
+    """apply one sparse multiplication per pair, ping-ponging between the two f buffers.
+    f_slots_cycle: list of classes the successive results go to."""
+    outs = []
+    for k, line in enumerate(lines_per_pair):
+        cls = f_slots_cycle[k]
+        nodes = sparse_mul_nodes(f_cur, line, cv.supp, pred=k + 1, alt=f_cur)
+        outs += bind(nodes, cls)
+        f_cur = nodes
+    return outs, f_cur
+
+
+def _double_pair(cv, k):
+    X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
+    P = ref(C_ABS, P_BASE + k)
+    XY = mul(X, Y, name='XY')
+    B = sqr(Y, name='B')
+    C = sqr(Z, name='C')
+    H = dot([((Y, DBL), Z)], name='H')
+    J = sqr(X, name='J')
+    if cv.btw_is_4xi:
+        E = lin([((C, XI), 12)], name='E')
+    else:
+        Cb = mul(C, const(K_BTW), name='Cb')
+        E = lin([(Cb, 3)], name='E')
+    F3 = lin([(E, 3)], name='F3')
+    Gv = lin([(B, 1), (E, 3)], halve=True, name='G')
+    BmF = lin([(B, 1), (E, -3)], name='BmF')
+    I = lin([(E, 1), (B, -1)], name='I')
+    X3 = dot([(XY, BmF)], halve=True, name='X3')
+    Y3 = dot([(Gv, Gv), (F3, (E, NEG))], name='Y3')
+    Z3 = mul(B, H, name='Z3')
+    if cv.twist == 'M':      # (r0,r1,r2) = (I, 3J, -H): w^0 = r0, w^2 = r1 xP, w^3 = r2 yP
+        line = {0: I, 2: dot([(J, (P, REAL0))], scale=3), 3: dot([((H, NEG), (P, REAL1))])}
+    else:                    # (r0,r1,r2) = (-H, 3J, I): w^0 = r0 yP, w^1 = r1 xP, w^3 = r2
+        line = {0: dot([((H, NEG), (P, REAL1))]), 1: dot([(J, (P, REAL0))], scale=3), 3: I}
+    tout = [(X3, (C_ABS, T_BASE + 3 * k)), (Y3, (C_ABS, T_BASE + 3 * k + 1)), (Z3, (C_ABS, T_BASE + 3 * k + 2))]
+    return tout, line
+
+
+def _add_pair(cv, k, qx, qy, update=True):
+    X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
+    P = ref(C_ABS, P_BASE + k)
+    O = dot([((qy, NEG), Z)], lin=[(Y, 1)], name='O')
+    L = dot([((qx, NEG), Z)], lin=[(X, 1)], name='L')
+    J = dot([(qx, O), ((L, NEG), qy)], name='J')
+    tout = []
+    if update:
+        Cc = sqr(O)
+        D = sqr(L)
+        E = mul(L, D)
+        Fv = mul(Z, Cc)
+        Gv = mul(X, D)
+        H = lin([(E, 1), (Fv, 1), (Gv, -2)])
+        GmH = lin([(Gv, 1), (H, -1)])
+        X3 = mul(L, H)
+        Y3 = dot([(GmH, O), ((Y, NEG), E)])
+        Z3 = mul(E, Z)
+        tout = [(X3, (C_ABS, T_BASE + 3 * k)), (Y3, (C_ABS, T_BASE + 3 * k + 1)), (Z3, (C_ABS, T_BASE + 3 * k + 2))]
+    if cv.twist == 'M':      # (J, -O, L)
+        line = {0: J, 2: dot([((O, NEG), (P, REAL0))]), 3: dot([(L, (P, REAL1))])}
+    else:                    # (L, -O, J)
+        line = {0: dot([(L, (P, REAL1))]), 1: dot([((O, NEG), (P, REAL0))]), 3: J}
+    return tout, line
+
+
+def _f_cycle(n):
+    """buffers the successive f results are written to, starting from a read of B1"""
+    return [C_B2 if i % 2 == 0 else C_B1 for i in range(n)]
+
+
+def prog_dbl(cv, np_):
+    f = regs(C_B1)
+    f2 = f12_sqr_nodes(f)
+    cyc = _f_cycle(1 + np_)
+    outs = bind(f2, cyc[0])
+    lines = []
+    for k in range(np_):
+        t, line = _double_pair(cv, k)
+        outs += t
+        lines.append(line)
+    so, _ = _line_and_sparse(cv, f2, lines, cyc[1:])
+    outs += so
+    return compile_program('DBL%d' % np_, outs, miller_temps())
+
+
+def prog_add(cv, np_):
+    f = regs(C_B1)
+    outs, lines = [], []
+    for k in range(np_):
+        qx = ref(C_ABS, Q_BASE + 3 * k)
+        qy = ref(C_B3, Q_BASE + 3 * k + 1)
+        t, line = _add_pair(cv, k, qx, qy)
+        outs += t
+        lines.append(line)
+    so, _ = _line_and_sparse(cv, f, lines, _f_cycle(np_))
+    outs += so
+    return compile_program('ADD%d' % np_, outs, miller_temps())
+
+
+def prog_bn_tail(cv, np_):
+    """f *= l_{T,pi(Q)}; T += pi(Q); f *= l_{T,-pi^2(Q)}   """
+    f = regs(C_B1)
+    f_cur = f
+    outs = []
+    cyc = _f_cycle(2 * np_)
+    ci = 0
+    for k in range(np_):
+        qx, qy = ref(C_ABS, Q_BASE + 3 * k), ref(C_ABS, Q_BASE + 3 * k + 1)
+        q1x = dot([((qx, CONJ), const(k_frob(1, 2)))])
+        q1y = dot([((qy, CONJ), const(k_frob(1, 3)))])
+        q2x = dot([(qx, const(k_frob(2, 2)))])
+        X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
+        P = ref(C_ABS, P_BASE + k)
+        # first step (with update), written out here because the second step needs the NEW T as DAG nodes
+        O = dot([((q1y, NEG), Z)], lin=[(Y, 1)])
+        L = dot([((q1x, NEG), Z)], lin=[(X, 1)])
+        J = dot([(q1x, O), ((L, NEG), q1y)])
+        Cc, D = sqr(O), sqr(L)
+        E, Fv, Gv = mul(L, D), mul(Z, Cc), mul(X, D)
+        H = lin([(E, 1), (Fv, 1), (Gv, -2)])
+        GmH = lin([(Gv, 1), (H, -1)])
+        X3, Y3, Z3 = mul(L, H), dot([(GmH, O), ((Y, NEG), E)]), mul(E, Z)
+        line1 = {0: dot([(L, (P, REAL1))]), 1: dot([((O, NEG), (P, REAL0))]), 3: J}
+        # second step, line only, through (X3,Y3,Z3) and (q2x, qy)
+        O2 = dot([((qy, NEG), Z3)], lin=[(Y3, 1)])
+        L2 = dot([((q2x, NEG), Z3)], lin=[(X3, 1)])
+        J2 = dot([(q2x, O2), ((L2, NEG), qy)])
+        line2 = {0: dot([(L2, (P, REAL1))]), 1: dot([((O2, NEG), (P, REAL0))]), 3: J2}
+        for line in (line1, line2):
+            nodes = sparse_mul_nodes(f_cur, line, cv.supp, pred=k + 1, alt=f_cur)
+            outs += bind(nodes, cyc[ci])
+            ci += 1
+            f_cur = nodes
+    return compile_program('BNTAIL%d' % np_, outs, miller_temps())
+
+
+def prog_init(np_):
+    """f = 1 (into B1), Z_k = 1, -y_k"""
+    one, zero = const(K_ONE), const(K_ZERO)
+    outs = [(lin([(one if k == 0 else zero, 1)]), (C_B1, k)) for k in range(6)]
+    for k in range(np_):
+        outs.append((lin([(one, 1)]), (C_ABS, T_BASE + 3 * k + 2)))
+        outs.append((lin([(ref(C_ABS, Q_BASE + 3 * k), 1)]), (C_ABS, T_BASE + 3 * k)))
+        outs.append((lin([(ref(C_ABS, Q_BASE + 3 * k + 1), 1)]), (C_ABS, T_BASE + 3 * k + 1)))
+        outs.append((lin([((ref(C_ABS, Q_BASE + 3 * k + 1), NEG), 1)]), (C_ABS, Q_BASE + 3 * k + 2)))
+    return compile_program('INIT%d' % np_, outs, miller_temps())
+
+
+def build_all(curve_name):
+    """name -> Program for one curve"""
+    cv = CURVES[curve_name]
+    _cfg['nslots'], _cfg['nregs'] = SLOTCFG[curve_name]
+    progs = {}
+    for np_ in (1, 2):
+        progs['INIT%d' % np_] = prog_init(np_)
+        progs['DBL%d' % np_] = prog_dbl(cv, np_)
+        progs['ADD%d' % np_] = prog_add(cv, np_)
+        if cv.family == 'bn':
+            progs['BNTAIL%d' % np_] = prog_bn_tail(cv, np_)
+    progs['F12_MUL'] = prog_f12_mul()
+    progs['CYCLO_SQR'] = prog_cyclo()
+    progs['CONJ'] = prog_conj()
+    for k in (1, 2, 3):
+        progs['FROB%d' % k] = prog_frob(k)
+    progs['F12_INV'] = prog_inv()
+    return progs

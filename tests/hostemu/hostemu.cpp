@@ -118,3 +118,40 @@ extern "C" int he_pairing_bytes(int curve, int np, const uint8_t* g1a, const uin
     if (curve == 1) return t_pair_bytes<BLS381>(np, g1a, g2a, g1b, g2b, out, fexp);
     return t_pair_bytes<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
 }
+
+#include "../../mathlib_b200/csrc/pairing_vm.cuh"
+#include <vector>
+// VM pairing on the host: lanes of a phase are executed one after another (pairing_vm.cuh, host path of run())
+template <class C> static int t_vm_pair(int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                                        uint8_t* out, int fexp) {
+    constexpr int N = C::N;
+    typedef VmTables<C> TB;
+    std::vector<uint32_t> slots((size_t)TB::NSLOTS * 2 * N, 0u), kb((size_t)VM_KBANK * 2 * N);
+    for (int i = 0; i < VM_KBANK; i++) vm_fill_kbank<C>(kb.data() + (size_t)i * 2 * N, i);
+    VmDriver<C> D;
+    D.ctx.slots = slots.data();
+    D.ctx.kbank = kb.data();
+    D.words = TB::host_words();
+    D.dir = TB::host_dir();
+    D.role = 0;
+    int err = 0;
+    unsigned m0 = 0, m1 = 0;
+    for (int r = 0; r < VM_G; r++) {
+        m0 |= (unsigned)D.load_coord(r, 0, g1a, g2a, false, &err) << r;
+        if (np == 2) m1 |= (unsigned)D.load_coord(r, 1, g1b, g2b, false, &err) << r;
+    }
+    if (err) return 1;
+    bool dead0 = ((m0 & 3u) == 3u) || ((m0 & 60u) == 60u);
+    bool dead1 = np == 2 ? (((m1 & 3u) == 3u) || ((m1 & 60u) == 60u)) : true;
+    D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
+    uint32_t fb = np == 1 ? D.template miller<1>() : D.template miller<2>();
+    if (fexp) fb = D.final_exp(fb);
+    for (int r = 0; r < VM_G; r++) D.store_coeff(r, fb, out, false);
+    return 0;
+}
+extern "C" int he_vm_pairing(int curve, int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                             uint8_t* out, int fexp) {
+    if (curve == 0) return t_vm_pair<BN254>(np, g1a, g2a, g1b, g2b, out, fexp);
+    if (curve == 1) return t_vm_pair<BLS381>(np, g1a, g2a, g1b, g2b, out, fexp);
+    return t_vm_pair<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
+}

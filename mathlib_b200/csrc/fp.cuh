@@ -275,12 +275,11 @@ struct FpOps {
         mul(r, a, o);
     }
 
-    // r = a^(p-2) (Fermat).  Not constant time; inputs are public here.
-    static B200_HD_NOINLINE void inv(E& r, const E& a) {
+    // r = a^(p-2) (Fermat).  Kept as the cross-check of inv() in the tests.
+    static B200_HD_NOINLINE void inv_fermat(E& r, const E& a) {
         const uint32_t* p = C::p();
         E acc, base = a;
         one(acc);
-        // exponent p-2, LSB first
         uint32_t borrow2 = 2;
         for (int i = 0; i < N; i++) {
             uint32_t w = p[i];
@@ -292,6 +291,59 @@ struct FpOps {
             }
         }
         r = acc;
+    }
+
+    // helpers on plain N-word integers
+    static B200_HD bool geq(const uint32_t* a, const uint32_t* b) {      // a >= b
+        uint32_t t = sub_cc(a[0], b[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t = subc_cc(a[i], b[i]);
+        (void)t;
+        return subc(0, 0) == 0;
+    }
+    static B200_HD void shr1(uint32_t* a) {
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+        a[N - 1] >>= 1;
+    }
+    static B200_HD void sub_n(uint32_t* a, const uint32_t* b) {           // a -= b (a >= b)
+        a[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) a[i] = subc_cc(a[i], b[i]);
+        a[N - 1] = subc(a[N - 1], b[N - 1]);
+    }
+
+    // r = a^-1 in Montgomery form (a = xR -> x^-1 R), binary extended Euclid on the ALU pipe:
+    // ~2*bits shift / subtract steps instead of ~1.5*bits Montgomery products, and it leaves the multiplier free.
+    // inv(0) = 0 (same convention as gnark's Inverse).  Not constant time; inputs are public here.
+    static B200_HD_NOINLINE void inv(E& r, const E& a) {
+        if (is_zero(a)) { zero(r); return; }
+        const uint32_t* p = C::p();
+        uint32_t u[N], v[N];
+        E x1, x2;
+#pragma unroll
+        for (int i = 0; i < N; i++) { u[i] = a.l[i]; v[i] = p[i]; x1.l[i] = 0; x2.l[i] = 0; }
+        x1.l[0] = 1;
+        // invariants: x1 * a == u, x2 * a == v (mod p)
+        for (;;) {
+            uint32_t u_is_one = u[0] ^ 1u, v_is_one = v[0] ^ 1u;
+#pragma unroll
+            for (int i = 1; i < N; i++) { u_is_one |= u[i]; v_is_one |= v[i]; }
+            if (u_is_one == 0 || v_is_one == 0) {
+                E res = (u_is_one == 0) ? x1 : x2;
+                // res = a^-1 (as integers mod p) = x^-1 R^-1 ; times R^3 / R -> x^-1 R
+                E r3;
+                const uint32_t* q = C::K().r3;
+#pragma unroll
+                for (int i = 0; i < N; i++) r3.l[i] = q[i];
+                mul(r, res, r3);
+                return;
+            }
+            while (!(u[0] & 1)) { shr1(u); halve(x1, x1); }
+            while (!(v[0] & 1)) { shr1(v); halve(x2, x2); }
+            if (geq(u, v)) { sub_n(u, v); sub(x1, x1, x2); }
+            else { sub_n(v, u); sub(x2, x2, x1); }
+        }
     }
 };
 

@@ -41,13 +41,25 @@ struct Vm {
         uint32_t b = cls == VM_C_ABS ? 0u : c.base[cls - 1];
         return c.slots + (b + idx) * SLOT_WORDS;
     }
+    // slots are 16-byte aligned (slot = 2N words, N a multiple of 4): 128-bit accesses
+    struct alignas(16) Q4 { uint32_t x, y, z, w; };
     static B200_HD void load2(E2& r, const uint32_t* p) {
+        const Q4* q = reinterpret_cast<const Q4*>(p);
 #pragma unroll
-        for (int i = 0; i < N; i++) { r.c0.l[i] = p[i]; r.c1.l[i] = p[N + i]; }
+        for (int i = 0; i < N / 4; i++) {
+            Q4 a = q[i], b = q[N / 4 + i];
+            r.c0.l[4 * i] = a.x; r.c0.l[4 * i + 1] = a.y; r.c0.l[4 * i + 2] = a.z; r.c0.l[4 * i + 3] = a.w;
+            r.c1.l[4 * i] = b.x; r.c1.l[4 * i + 1] = b.y; r.c1.l[4 * i + 2] = b.z; r.c1.l[4 * i + 3] = b.w;
+        }
     }
     static B200_HD void store2(uint32_t* p, const E2& r) {
+        Q4* q = reinterpret_cast<Q4*>(p);
 #pragma unroll
-        for (int i = 0; i < N; i++) { p[i] = r.c0.l[i]; p[N + i] = r.c1.l[i]; }
+        for (int i = 0; i < N / 4; i++) {
+            Q4 a = {r.c0.l[4 * i], r.c0.l[4 * i + 1], r.c0.l[4 * i + 2], r.c0.l[4 * i + 3]};
+            Q4 b = {r.c1.l[4 * i], r.c1.l[4 * i + 1], r.c1.l[4 * i + 2], r.c1.l[4 * i + 3]};
+            q[i] = a; q[N / 4 + i] = b;
+        }
     }
     // modifiers in the order CONJ, XI, DBL, NEG; result fully reduced
     static B200_HD void apply_mod(E2& x, uint32_t m) {
@@ -60,105 +72,122 @@ struct Vm {
     // ---------------------------------------------------------------------------------------------------
     // wide arithmetic
     // ---------------------------------------------------------------------------------------------------
-    // v[0..2N) = a * b (fresh), a, b < 2^(32N)
-    static B200_HD void wide_mul(uint32_t* v, const uint32_t* a, const uint32_t* b) {
-        uint32_t Ev[2 * N + 2], Od[2 * N + 2];
+    static constexpr int AW = 2 * N + 2;         // words of an even / odd accumulator array
+    // Product-scanning multiply-accumulate of up to three independent wide accumulators in lock-step:
+    //   X += a0*b0,  Y += a1*b1 (skipped when !with_y),  Z += sa*sb          (all unreduced, W words each)
+    // Column k collects the products a[i]*b[k-i] in a 96-bit running sum (c0,c1,c2): one IMAD.WIDE.U32 (carry out)
+    // plus one IADD3.X per product.  Each accumulator is one dependent chain; running the three side by side gives
+    // the FMA-heavy pipe three independent chains per warp and needs no temporary product arrays.
+    static B200_HD void wide_mac3(uint32_t* X, uint32_t* Y, uint32_t* Z, const uint32_t* a0, const uint32_t* b0,
+                                  const uint32_t* a1, const uint32_t* b1, const uint32_t* sa, const uint32_t* sb,
+                                  bool with_y) {
+        uint32_t x0 = X[0], x1 = X[1], x2 = 0;
+        uint32_t y0 = Y[0], y1 = Y[1], y2 = 0;
+        uint32_t z0 = Z[0], z1 = Z[1], z2 = 0;
 #pragma unroll
-        for (int i = 0; i < 2 * N + 2; i++) { Ev[i] = 0; Od[i] = 0; }
+        for (int k = 0; k < 2 * N - 1; k++) {
 #pragma unroll
-        for (int i = 0; i < N; i++) {
-            // products a[j]*b[i] land on word i+j: even (i+j) -> Ev, odd -> Od (Od[k] holds word k+1)
-            const int je = i & 1;          // first j with (i+j) even
-            const int jo = je ^ 1;         // first j with (i+j) odd
-            {   // even-aligned chain, words i+je .. i+je+N-1
-                const int w0 = i + je;
-                Ev[w0] = mad_lo_cc(a[je], b[i], Ev[w0]);
-                Ev[w0 + 1] = madc_hi_cc(a[je], b[i], Ev[w0 + 1]);
-#pragma unroll
-                for (int j = je + 2; j < N; j += 2) {
-                    Ev[i + j] = madc_lo_cc(a[j], b[i], Ev[i + j]);
-                    Ev[i + j + 1] = madc_hi_cc(a[j], b[i], Ev[i + j + 1]);
-                }
-                Ev[w0 + N] = addc(Ev[w0 + N], 0);
+            for (int i = (k < N ? 0 : k - N + 1); i <= (k < N ? k : N - 1); i++) {
+                const int j = k - i;
+                x0 = mad_lo_cc(a0[i], b0[j], x0); x1 = madc_hi_cc(a0[i], b0[j], x1); x2 = addc(x2, 0);
+                if (with_y) { y0 = mad_lo_cc(a1[i], b1[j], y0); y1 = madc_hi_cc(a1[i], b1[j], y1); y2 = addc(y2, 0); }
+                z0 = mad_lo_cc(sa[i], sb[j], z0); z1 = madc_hi_cc(sa[i], sb[j], z1); z2 = addc(z2, 0);
             }
-            {   // odd-aligned chain: product at word i+jo (odd) is stored at Od[i+jo-1]
-                const int w0 = i + jo - 1;
-                Od[w0] = mad_lo_cc(a[jo], b[i], Od[w0]);
-                Od[w0 + 1] = madc_hi_cc(a[jo], b[i], Od[w0 + 1]);
-#pragma unroll
-                for (int j = jo + 2; j < N; j += 2) {
-                    Od[i + j - 1] = madc_lo_cc(a[j], b[i], Od[i + j - 1]);
-                    Od[i + j] = madc_hi_cc(a[j], b[i], Od[i + j]);
-                }
-                Od[w0 + N] = addc(Od[w0 + N], 0);
-            }
+            X[k] = x0; x0 = x1; x1 = add_cc(x2, X[k + 2]); x2 = addc(0, 0);
+            if (with_y) { Y[k] = y0; y0 = y1; y1 = add_cc(y2, Y[k + 2]); y2 = addc(0, 0); }
+            Z[k] = z0; z0 = z1; z1 = add_cc(z2, Z[k + 2]); z2 = addc(0, 0);
         }
-        // v = Ev + (Od << 32)
+        X[2 * N - 1] = x0; X[2 * N] = x1;
+        if (with_y) { Y[2 * N - 1] = y0; Y[2 * N] = y1; }
+        Z[2 * N - 1] = z0; Z[2 * N] = z1;
+    }
+    // v[0..W) = Ev + (Od << 32)
+    static B200_HD void wide_merge(uint32_t* v, const uint32_t* Ev, const uint32_t* Od) {
         v[0] = Ev[0];
         v[1] = add_cc(Ev[1], Od[0]);
 #pragma unroll
-        for (int k = 2; k < 2 * N - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
-        v[2 * N - 1] = addc(Ev[2 * N - 1], Od[2 * N - 2]);
+        for (int k = 2; k < W - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
+        v[W - 1] = addc(Ev[W - 1], Od[W - 2]);
     }
-    // acc[0..W) += v[0..2N)
     static B200_HD void wide_add(uint32_t* acc, const uint32_t* v) {
         acc[0] = add_cc(acc[0], v[0]);
 #pragma unroll
-        for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], v[k]);
-        acc[2 * N] = addc(acc[2 * N], 0);
+        for (int k = 1; k < W - 1; k++) acc[k] = addc_cc(acc[k], v[k]);
+        acc[W - 1] = addc(acc[W - 1], v[W - 1]);
     }
     static B200_HD void wide_sub(uint32_t* acc, const uint32_t* v) {
         acc[0] = sub_cc(acc[0], v[0]);
 #pragma unroll
-        for (int k = 1; k < 2 * N; k++) acc[k] = subc_cc(acc[k], v[k]);
-        acc[2 * N] = subc(acc[2 * N], 0);
+        for (int k = 1; k < W - 1; k++) acc[k] = subc_cc(acc[k], v[k]);
+        acc[W - 1] = subc(acc[W - 1], v[W - 1]);
     }
-    // Montgomery reduction of a wide value T < 4 p R  ->  canonical residue T / R mod p
+    // Montgomery reduction of a wide value T < 4 p R (T[0..2N), top word zero) -> canonical residue T / R mod p.
+    // Word-sliding reduction on an even / odd split of T: no data movement, the window offsets are compile-time.
     static B200_HD void redc(E1& r, const uint32_t* Tw) {
-        const uint32_t* p = C::p();
-        // REDC(T_low) via the reduction rows of FpOps::mul (no a*b part), then + T_high
-        uint32_t X[N + 2], Y[N + 2];
+        uint32_t X[AW], Y[AW];
 #pragma unroll
-        for (int j = 0; j < N; j += 2) { X[j] = Tw[j]; X[j + 1] = 0; Y[j] = Tw[j + 1]; Y[j + 1] = 0; }
-        X[N] = 0; X[N + 1] = 0; Y[N] = 0; Y[N + 1] = 0;
+        for (int k = 0; k < 2 * N; k += 2) { X[k] = Tw[k]; X[k + 1] = 0; Y[k] = Tw[k + 1]; Y[k + 1] = 0; }
+        X[2 * N] = 0; X[2 * N + 1] = 0; Y[2 * N] = 0; Y[2 * N + 1] = 0;
+        const uint32_t* p = C::p();
         {
             uint32_t m = mul_lo(X[0], C::inv32());
-            F::chain_odd(Y, p, m);
-            F::chain_even(X, p, m);
-            X[N] = addc(0, 0);
+            chain_odd_full(Y, p, m, false);
+            chain_even_full(X, p, m);
         }
+        // after row i the even accumulator's word 0 is zero; its word 1 is folded into the other accumulator and
+        // the roles swap with the old even accumulator sliding up by two words
 #pragma unroll
-        for (int i = 1; i < N; i += 2) {
-            redc_row(X, Y);
-            if (i + 1 < N) redc_row(Y, X);
+        for (int i = 1; i < N; i++) {
+            const int ao = 2 * ((i - 1) / 2) + ((i & 1) ? 0 : 0);
+            if (i & 1) {      // A = X (window at xo), B = Y (window at yo)
+                const int xo = i - 1, yo = i - 1;
+                Y[yo] = add_cc(Y[yo], X[xo + 1]);
+                uint32_t m = mul_lo(Y[yo], C::inv32());
+                chain_odd_full(X + xo + 2, p, m, true);
+                chain_even_full(Y + yo, p, m);
+            } else {          // A = Y, B = X
+                const int yo = i - 2, xo = i;
+                X[xo] = add_cc(X[xo], Y[yo + 1]);
+                uint32_t m = mul_lo(X[xo], C::inv32());
+                chain_odd_full(Y + yo + 2, p, m, true);
+                chain_even_full(X + xo, p, m);
+            }
+            (void)ao;
         }
-        E1 lo;
-        lo.l[0] = add_cc(X[0], Y[1]);
+        // N rows done (N even): the last row had A = X at offset N-2 -> X slid to N, B = Y at offset N-2.
+        // result word k = Yw[k+1] + Xw[k] with Yw = Y + (N-2) (even accumulator), Xw = X + N (odd accumulator)
+        const uint32_t* Yw = Y + (N - 2);
+        const uint32_t* Xw = X + N;
+        r.l[0] = add_cc(Xw[0], Yw[1]);
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) lo.l[i] = addc_cc(X[i], Y[i + 1]);
-        lo.l[N - 1] = addc(X[N - 1], Y[N]);
-        // + T_high (N words; T < 4pR so the sum is < 5p < 2^(32N))
-        r.l[0] = add_cc(lo.l[0], Tw[N]);
-#pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(lo.l[i], Tw[N + i]);
-        r.l[N - 1] = addc(lo.l[N - 1], Tw[2 * N - 1]);
-        // canonicalise: r < 4p -> subtract 2p, then p, conditionally
+        for (int k = 1; k < N - 1; k++) r.l[k] = addc_cc(Xw[k], Yw[k + 1]);
+        r.l[N - 1] = addc(Xw[N - 1], Yw[N]);
         cond_sub_kp(r, 1);
         cond_sub_kp(r, 0);
     }
-    // row of the reduction without a multiplicand part: A = previous even accumulator, B = previous odd accumulator
-    static B200_HD void redc_row(uint32_t* A, uint32_t* B) {
-        const uint32_t* p = C::p();
-        B[0] = add_cc(B[0], A[1]);
+    // acc (even aligned, full-size words above) += v_even * m, carry rippled one word up
+    static B200_HD void chain_even_full(uint32_t* acc, const uint32_t* v, uint32_t m) {
+        acc[0] = mad_lo_cc(v[0], m, acc[0]);
+        acc[1] = madc_hi_cc(v[0], m, acc[1]);
 #pragma unroll
-        for (int j = 0; j < N - 2; j++) A[j] = addc_cc(A[j + 2], 0);
-        A[N - 2] = addc(A[N], 0);
-        A[N - 1] = 0;
-        B[N] = 0;
-        uint32_t m = mul_lo(B[0], C::inv32());
-        F::chain_odd(A, p, m);
-        F::chain_even(B, p, m);
-        B[N] = addc(B[N], 0);
+        for (int j = 2; j < N; j += 2) {
+            acc[j] = madc_lo_cc(v[j], m, acc[j]);
+            acc[j + 1] = madc_hi_cc(v[j], m, acc[j + 1]);
+        }
+        acc[N] = addc_cc(acc[N], 0);
+        acc[N + 1] = addc(acc[N + 1], 0);
+    }
+    // acc (odd aligned) += v_odd * m; optional carry-in from the preceding stray-word addition
+    static B200_HD void chain_odd_full(uint32_t* acc, const uint32_t* v, uint32_t m, bool carry_in) {
+        if (carry_in) acc[0] = madc_lo_cc(v[1], m, acc[0]); else acc[0] = mad_lo_cc(v[1], m, acc[0]);
+        acc[1] = madc_hi_cc(v[1], m, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            acc[j] = madc_lo_cc(v[j + 1], m, acc[j]);
+            acc[j + 1] = madc_hi_cc(v[j + 1], m, acc[j + 1]);
+        }
+        acc[N] = addc_cc(acc[N], 0);
+        acc[N + 1] = addc(acc[N + 1], 0);
     }
     // r -= (p << sh) if r >= (p << sh)
     static B200_HD void cond_sub_kp(E1& r, int sh) {
@@ -213,49 +242,48 @@ struct Vm {
             return;
         }
         if (kind == VM_DOT) {
-            uint32_t RE[W], IM[W];
-            // RE starts at nt * |BETA| * p^2 so that the subtractions below never underflow
-            {
-                const uint32_t* off = C::K().p2 + (nt * (C::BETA == -1 ? 1 : 5)) * (2 * N);
+            // X = sum a0 b0, Y = sum a1 b1, Z = sum (a0+a1)(b0+b1), all unreduced
+            uint32_t Xm[W], Ym[W], IM[W];
 #pragma unroll
-                for (int k = 0; k < 2 * N; k++) { RE[k] = off[k]; IM[k] = 0; }
-                RE[2 * N] = 0; IM[2 * N] = 0;
-            }
+            for (int k = 0; k < W; k++) { Xm[k] = 0; Ym[k] = 0; IM[k] = 0; }
             for (uint32_t t = 0; t < nt; t++) {
                 const uint32_t tw = w[2 + t];
                 E2 a, b;
                 load2(a, operand_ptr(c, tw & 0x7FF));
-                apply_mod(a, (tw >> 22) & 15);
+                const uint32_t am = (tw >> 22) & 15;
+                if (am) apply_mod(a, am);
                 const uint32_t bm = (tw >> 26) & 15;
                 load2(b, operand_ptr(c, (tw >> 11) & 0x7FF));
                 const bool real_b = (bm & (VM_REAL0 | VM_REAL1)) != 0;
                 if (real_b) {
                     if (bm & VM_REAL1) b.c0 = b.c1;
-                } else {
+                    F::zero(b.c1);
+                } else if (bm & 3) {
                     apply_mod(b, bm & 3);
                 }
-                uint32_t v[2 * N];
-                wide_mul(v, a.c0.l, b.c0.l);               // v0 = a0 b0
-                wide_add(RE, v);
-                if (!real_b) {
-                    wide_sub(IM, v);
-                    wide_mul(v, a.c1.l, b.c1.l);           // v1 = a1 b1
-                    wide_sub(IM, v);
-                    wide_sub(RE, v);
-                    if (C::BETA == -5) { wide_sub(RE, v); wide_sub(RE, v); wide_sub(RE, v); wide_sub(RE, v); }
-                    // (a0+a1)(b0+b1): sums stay below 2p < 2^(32N)
-                    a.c0.l[0] = add_cc(a.c0.l[0], a.c1.l[0]);
+                // sums (a0+a1), (b0+b1) stay below 2p < 2^(32N); for a real b this is (a0+a1) * s
+                uint32_t sa[N], sb[N];
+                sa[0] = add_cc(a.c0.l[0], a.c1.l[0]);
 #pragma unroll
-                    for (int i = 1; i < N; i++) a.c0.l[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
-                    b.c0.l[0] = add_cc(b.c0.l[0], b.c1.l[0]);
+                for (int i = 1; i < N; i++) sa[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
+                sb[0] = add_cc(b.c0.l[0], b.c1.l[0]);
 #pragma unroll
-                    for (int i = 1; i < N; i++) b.c0.l[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
-                    wide_mul(v, a.c0.l, b.c0.l);
-                    wide_add(IM, v);
-                } else {
-                    wide_mul(v, a.c1.l, b.c0.l);           // imaginary part a1 * s
-                    wide_add(IM, v);
-                }
+                for (int i = 1; i < N; i++) sb[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
+                if (real_b) wide_mac3(Xm, Ym, IM, a.c0.l, b.c0.l, a.c1.l, b.c1.l, sa, sb, false);
+                else wide_mac3(Xm, Ym, IM, a.c0.l, b.c0.l, a.c1.l, b.c1.l, sa, sb, true);
+            }
+            uint32_t RE[W];
+            {
+                wide_sub(IM, Xm);
+                wide_sub(IM, Ym);                           // IM = Z - X - Y >= 0
+                // RE = X + nt*|BETA|*p^2 - |BETA|*Y  (offset keeps it non-negative, multiple of p)
+                const uint32_t* off = C::K().p2 + (nt * (C::BETA == -1 ? 1 : 5)) * (2 * N);
+#pragma unroll
+                for (int k = 0; k < 2 * N; k++) RE[k] = off[k];
+                RE[2 * N] = 0;
+                wide_add(RE, Xm);
+                wide_sub(RE, Ym);
+                if (C::BETA == -5) { wide_sub(RE, Ym); wide_sub(RE, Ym); wide_sub(RE, Ym); wide_sub(RE, Ym); }
             }
             redc(res.c0, RE);
             redc(res.c1, IM);

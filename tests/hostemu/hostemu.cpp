@@ -13,6 +13,7 @@ template <class C> static void t_mul(const uint32_t* a, const uint32_t* b, uint3
         case 3: F::neg(z, x); break;
         case 4: F::halve(z, x); break;
         case 5: F::inv(z, x); break;
+        case 8: F::inv_fermat(z, x); break;
         case 6: F::to_mont(z, x); break;
         case 7: F::from_mont(z, x); break;
     }

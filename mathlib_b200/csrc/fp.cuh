@@ -259,6 +259,9 @@ struct FpOps {
         reduce_once(r);
     }
     static B200_HD void sqr(E& r, const E& a) { mul(r, a, a); }
+    // out-of-line product for callers whose hot loop must stay inside the instruction cache (G1 point formulas)
+    static B200_HD_NOINLINE void mulx(E& r, const E& a, const E& b) { mul(r, a, b); }
+    static B200_HD void sqrx(E& r, const E& a) { mulx(r, a, a); }
 
     // Montgomery form conversions
     static B200_HD void to_mont(E& r, const E& a) {

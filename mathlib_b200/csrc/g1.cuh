@@ -35,20 +35,20 @@ struct G1Ops {
     static B200_HD void neg(Pt& r, const Pt& a) { r.x = a.x; F::neg(r.y, a.y); r.zz = a.zz; r.zzz = a.zzz; }
 
     // p <- 2a for affine a (mdbl-2008-s-1)
-    static B200_HD void dbl_affine(Pt& p, const Aff& a) {
+    static B200_HD_NOINLINE void dbl_affine(Pt& p, const Aff& a) {
         if (aff_is_inf(a) || F::is_zero(a.y)) { set_inf(p); return; }
         E U, V, W, S, M, t;
         F::dbl(U, a.y);
-        F::sqr(V, U);
-        F::mul(W, U, V);
-        F::mul(S, a.x, V);
-        F::sqr(M, a.x);
+        F::sqrx(V, U);
+        F::mulx(W, U, V);
+        F::mulx(S, a.x, V);
+        F::sqrx(M, a.x);
         F::dbl(t, M); F::add(M, M, t);
-        F::sqr(p.x, M);
+        F::sqrx(p.x, M);
         F::sub(p.x, p.x, S); F::sub(p.x, p.x, S);
         F::sub(t, S, p.x);
-        F::mul(t, M, t);
-        F::mul(U, W, a.y);
+        F::mulx(t, M, t);
+        F::mulx(U, W, a.y);
         F::sub(p.y, t, U);
         p.zz = V;
         p.zzz = W;
@@ -58,86 +58,86 @@ struct G1Ops {
         if (is_inf(p)) return;
         E U, V, W, S, M, t;
         F::dbl(U, p.y);
-        F::sqr(V, U);
-        F::mul(W, U, V);
-        F::mul(S, p.x, V);
-        F::sqr(M, p.x);
+        F::sqrx(V, U);
+        F::mulx(W, U, V);
+        F::mulx(S, p.x, V);
+        F::sqrx(M, p.x);
         F::dbl(t, M); F::add(M, M, t);
-        F::mul(U, W, p.y);            // W*Y1
-        F::sqr(p.x, M);
+        F::mulx(U, W, p.y);            // W*Y1
+        F::sqrx(p.x, M);
         F::sub(p.x, p.x, S); F::sub(p.x, p.x, S);
         F::sub(t, S, p.x);
-        F::mul(t, M, t);
+        F::mulx(t, M, t);
         F::sub(p.y, t, U);
-        F::mul(p.zz, V, p.zz);
-        F::mul(p.zzz, W, p.zzz);
+        F::mulx(p.zz, V, p.zz);
+        F::mulx(p.zzz, W, p.zzz);
     }
     // p <- p + a, a affine (madd-2008-s), complete
     static B200_HD_NOINLINE void madd(Pt& p, const Aff& a) {
         if (aff_is_inf(a)) return;
         if (is_inf(p)) { from_affine(p, a); return; }
         E U2, S2, Pp, R, PP, PPP, Q, t;
-        F::mul(U2, a.x, p.zz);
-        F::mul(S2, a.y, p.zzz);
+        F::mulx(U2, a.x, p.zz);
+        F::mulx(S2, a.y, p.zzz);
         F::sub(Pp, U2, p.x);
         F::sub(R, S2, p.y);
         if (F::is_zero(Pp)) {
             if (F::is_zero(R)) dbl_affine(p, a); else set_inf(p);
             return;
         }
-        F::sqr(PP, Pp);
-        F::mul(PPP, Pp, PP);
-        F::mul(Q, p.x, PP);
-        F::sqr(t, R);
+        F::sqrx(PP, Pp);
+        F::mulx(PPP, Pp, PP);
+        F::mulx(Q, p.x, PP);
+        F::sqrx(t, R);
         F::sub(t, t, PPP); F::sub(t, t, Q); F::sub(t, t, Q);   // X3
         F::sub(Q, Q, t);
-        F::mul(Q, R, Q);
-        F::mul(S2, p.y, PPP);
+        F::mulx(Q, R, Q);
+        F::mulx(S2, p.y, PPP);
         F::sub(p.y, Q, S2);
         p.x = t;
-        F::mul(p.zz, p.zz, PP);
-        F::mul(p.zzz, p.zzz, PPP);
+        F::mulx(p.zz, p.zz, PP);
+        F::mulx(p.zzz, p.zzz, PPP);
     }
     // p <- p + q (add-2008-s), complete
     static B200_HD_NOINLINE void add(Pt& p, const Pt& q) {
         if (is_inf(q)) return;
         if (is_inf(p)) { p = q; return; }
         E U1, U2, S1, S2, Pp, R, PP, PPP, Q, t;
-        F::mul(U1, p.x, q.zz);
-        F::mul(U2, q.x, p.zz);
-        F::mul(S1, p.y, q.zzz);
-        F::mul(S2, q.y, p.zzz);
+        F::mulx(U1, p.x, q.zz);
+        F::mulx(U2, q.x, p.zz);
+        F::mulx(S1, p.y, q.zzz);
+        F::mulx(S2, q.y, p.zzz);
         F::sub(Pp, U2, U1);
         F::sub(R, S2, S1);
         if (F::is_zero(Pp)) {
             if (F::is_zero(R)) dbl(p); else set_inf(p);
             return;
         }
-        F::sqr(PP, Pp);
-        F::mul(PPP, Pp, PP);
-        F::mul(Q, U1, PP);
-        F::sqr(t, R);
+        F::sqrx(PP, Pp);
+        F::mulx(PPP, Pp, PP);
+        F::mulx(Q, U1, PP);
+        F::sqrx(t, R);
         F::sub(t, t, PPP); F::sub(t, t, Q); F::sub(t, t, Q);   // X3
         F::sub(Q, Q, t);
-        F::mul(Q, R, Q);
-        F::mul(S1, S1, PPP);
+        F::mulx(Q, R, Q);
+        F::mulx(S1, S1, PPP);
         F::sub(p.y, Q, S1);
         p.x = t;
-        F::mul(p.zz, p.zz, q.zz);
-        F::mul(p.zz, p.zz, PP);
-        F::mul(p.zzz, p.zzz, q.zzz);
-        F::mul(p.zzz, p.zzz, PPP);
+        F::mulx(p.zz, p.zz, q.zz);
+        F::mulx(p.zz, p.zz, PP);
+        F::mulx(p.zzz, p.zzz, q.zzz);
+        F::mulx(p.zzz, p.zzz, PPP);
     }
     // affine (x,y) = (X/ZZ, Y/ZZZ); infinity -> (0,0)
     static B200_HD void to_affine(Aff& a, const Pt& p) {
         if (is_inf(p)) { F::zero(a.x); F::zero(a.y); return; }
         E t, i;
-        F::mul(t, p.zz, p.zzz);
+        F::mulx(t, p.zz, p.zzz);
         F::inv(i, t);
-        F::mul(t, i, p.zzz);      // 1/ZZ
-        F::mul(a.x, p.x, t);
-        F::mul(t, i, p.zz);       // 1/ZZZ
-        F::mul(a.y, p.y, t);
+        F::mulx(t, i, p.zzz);      // 1/ZZ
+        F::mulx(a.x, p.x, t);
+        F::mulx(t, i, p.zz);       // 1/ZZZ
+        F::mulx(a.y, p.y, t);
     }
 
     // scalar: 8 little-endian 32-bit words (any 256-bit value; [k]P = [k mod r]P in the r-torsion)

@@ -130,7 +130,7 @@ static __global__ void msm_scatter_kernel(size_t n, MsmPlan pl, const uint32_t* 
 }
 
 template <class C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 2)
 msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
                       const uint32_t* sorted, G1XYZZ<C::N>* buckets) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,9 +141,15 @@ msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uin
     uint32_t cnt = counts[t];
     typename G::Pt acc;
     G::set_inf(acc);
+    // software prefetch: the gather of point j+1 (index read + 2*FpBytes random read out of L2/HBM) is issued before
+    // the mixed addition of point j
+    typename G::Aff nxt;
+    uint32_t e_nxt = 0;
+    if (cnt) { e_nxt = run[0]; nxt = pts[e_nxt >> 1]; }
     for (uint32_t j = 0; j < cnt; j++) {
-        uint32_t e = run[j];
-        typename G::Aff a = pts[e >> 1];
+        typename G::Aff a = nxt;
+        const uint32_t e = e_nxt;
+        if (j + 1 < cnt) { e_nxt = run[j + 1]; nxt = pts[e_nxt >> 1]; }
         if (e & 1) FpOps<C>::neg(a.y, a.y);
         G::madd(acc, a);
     }

@@ -1,0 +1,122 @@
+"""GPU parity at sizes the C++ CPU oracle finishes in seconds, on seeded random inputs, plus size-independent
+properties at BASELINE.json's full batch sizes (bilinearity-derived unity checks, MSM linearity)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mathlib_b200
+    mathlib_b200.load()
+    return mathlib_b200
+
+
+def rand_inputs(m, cid, n, seed):
+    import bench
+    return bench.make_inputs(m, cid, n, seed=seed)
+
+
+@pytest.mark.parametrize("cid", [1, 3, 4, 5])
+def test_pairing2_random_vs_cpu_oracle(m, cid):
+    """1,000 random Pairing2 (+FExp) per curve id, raw and exponentiated bytes, against oracle/cpu."""
+    from oracle import cpu_binding as orc
+    c = m.Curves[cid]
+    n = 1000
+    g1a, g2a, g1b, g2b, expect = rand_inputs(m, cid, n, seed=100 + cid)
+    raw = c.Pairing2Batch(g1a, g2a, g1b, g2b, n)
+    assert raw == orc.pairing_batch(cid, n, g1a, g2a, g1b, g2b)
+    fe = c.FExpBatch(raw, n)
+    want = orc.pairing_batch(cid, n, g1a, g2a, g1b, g2b, fexp=True)
+    assert fe == want
+    assert c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP) == want
+    ver = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP | m.OUT_UNITY_ONLY)
+    assert list(ver) == list(expect)
+    # single pairing path
+    raw1 = c.PairingBatch(g1a, g2a, n)
+    assert raw1 == orc.pairing_batch(cid, n, g1a, g2a)
+
+
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_g1_mul_random_vs_cpu_oracle(m, cid):
+    from oracle import cpu_binding as orc
+    c = m.Curves[cid]
+    n = 4096
+    rnd = random.Random(7 + cid)
+    g1a, _, g1b, _, _ = rand_inputs(m, cid, n, seed=200 + cid)
+    ks = b"".join(rnd.randrange(1 << 256).to_bytes(32, "big") for _ in range(n))
+    ks2 = b"".join(rnd.randrange(c.order).to_bytes(32, "big") for _ in range(n))
+    out = b"".join(p.Bytes() for p in c.G1MulBatch(g1a, ks, n))
+    assert out == orc.g1_mul_batch(cid, n, g1a, ks)
+    out2 = b"".join(p.Bytes() for p in c.G1Mul2Batch(g1a, ks, g1b, ks2, n))
+    assert out2 == orc.g1_mul2_batch(cid, n, g1a, ks, g1b, ks2)
+
+
+@pytest.mark.parametrize("cid,n", [(5, 1), (5, 7), (5, 1000), (5, 1 << 14), (1, 1 << 14), (4, 1 << 13), (3, 300)])
+def test_msm_random_vs_cpu_oracle(m, cid, n):
+    from oracle import cpu_binding as orc
+    c = m.Curves[cid]
+    rnd = random.Random(n + cid)
+    g1a, _, _, _, _ = rand_inputs(m, cid, n, seed=300 + cid)
+    ks = b"".join(rnd.randrange(c.order).to_bytes(32, "big") for _ in range(n))
+    assert c.MsmBatch(g1a, ks, n) == orc.g1_msm(cid, n, g1a, ks)
+
+
+def test_msm_skewed_scalars(m):
+    """small / repeated scalars put most points into a few buckets (the reference tests use MaxInt64 scalars,
+    math_test.go:749-771): results must still be exact."""
+    from oracle import cpu_binding as orc
+    c = m.Curves[5]
+    n = 2048
+    g1a, _, _, _, _ = rand_inputs(m, 5, n, seed=401)
+    ks = b"".join((((1 << 63) - 1) if i % 3 else 5).to_bytes(32, "big") for i in range(n))
+    assert c.MsmBatch(g1a, ks, n) == orc.g1_msm(5, n, g1a, ks)
+
+
+def test_full_size_properties(m):
+    """BASELINE sizes: 65,536 BLS12-381 checks -- every even check is a valid BLS-style equation and must be 1, every odd
+    one must not; MSM 2^18 linearity: msm(P, k) + msm(P, k') == msm(P, k + k')."""
+    c = m.Curves[3]
+    n = 65536
+    g1a, g2a, g1b, g2b, expect = rand_inputs(m, 3, n, seed=55)
+    ver = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP | m.OUT_UNITY_ONLY)
+    assert (np.frombuffer(ver, dtype=np.uint8) == expect).all()
+    c5 = m.Curves[5]
+    nm = 1 << 18
+    rnd = np.random.default_rng(9)
+    pts = g1a * (nm // n)
+    k1 = rnd.integers(0, 256, size=(nm, 32), dtype=np.uint8)
+    k2 = rnd.integers(0, 256, size=(nm, 32), dtype=np.uint8)
+    k1[:, 0] &= 0x1F
+    k2[:, 0] &= 0x1F
+    s = (k1.astype(np.uint16)[:, ::-1] + k2.astype(np.uint16)[:, ::-1])
+    carry = np.zeros(nm, dtype=np.uint16)
+    ksum = np.zeros((nm, 32), dtype=np.uint8)
+    for j in range(32):
+        t = s[:, j] + carry
+        ksum[:, 31 - j] = (t & 0xFF).astype(np.uint8)
+        carry = t >> 8
+    a = c5.NewG1FromBytes(c5.MsmBatch(pts, k1.tobytes(), nm))
+    b = c5.NewG1FromBytes(c5.MsmBatch(pts, k2.tobytes(), nm))
+    a.Add(b)
+    assert a.Bytes() == c5.MsmBatch(pts, ksum.tobytes(), nm)
+
+
+def test_multi_gpu_split_matches_single(m):
+    """host-buffer batch calls split by index over every visible GPU; results must not depend on the split."""
+    lib = m.load()
+    if lib.b200_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c = m.Curves[5]
+    n = 4096
+    g1a, g2a, g1b, g2b, _ = rand_inputs(m, 5, n, seed=77)
+    multi = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP)
+    m.check(lib.b200_set_device(0))
+    single = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP)
+    assert multi == single

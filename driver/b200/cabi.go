@@ -1,0 +1,94 @@
+// Package b200 is a mathlib driver backed by hand-written sm_100a CUDA kernels (libb200math.so).
+//
+// It implements driver.Curve / driver.G1 / driver.G2 / driver.Gt / driver.Zr (reference driver/math.go:49-360)
+// and forwards the data-parallel hot path -- Pairing, Pairing2, FExp, MultiScalarMul, G1.Mul, G1.Mul2 and their
+// batch forms -- through cgo to the C ABI declared in include/b200.h.  Everything else (Zr arithmetic, hashing,
+// element bookkeeping) is thin host code.
+//
+// NOTE: this package was written against the header without a Go toolchain (none exists in the build image), so it
+// has never been compiled.  It is deliberately mechanical: each method marshals byte slabs and calls one C function.
+package b200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../mathlib_b200 -lb200math -Wl,-rpath,${SRCDIR}/../../mathlib_b200
+#include <stdlib.h>
+#include "b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"unsafe"
+)
+
+// flags (include/b200.h)
+const (
+	flagFExp      = 0x1
+	flagInMont    = 0x2
+	flagOutMont   = 0x4
+	flagUnityOnly = 0x8
+)
+
+func lastError() string { return C.GoString(C.b200_last_error()) }
+
+// check turns a non-zero return code into the panic the reference drivers raise
+// (reference driver/gurvy/bn254.go:249-251: panic(fmt.Sprintf("pairing failed [%s]", err))).
+func check(op string, rc C.int) {
+	if rc != 0 {
+		panic(fmt.Sprintf("%s failed [%s]", op, lastError()))
+	}
+}
+
+func ptr(b []byte) unsafe.Pointer {
+	if len(b) == 0 {
+		return nil
+	}
+	return unsafe.Pointer(&b[0])
+}
+
+// Init selects the GPUs (bit i = CUDA device i; 0 = all).  Optional: the first call initialises lazily.
+func Init(deviceMask uint32) { check("b200 init", C.b200_init(C.uint32_t(deviceMask))) }
+
+// pairingBatch: n x Pairing(G2,G1); g1 / g2 are contiguous slabs in the reference Bytes() encoding.
+func pairingBatch(curve int, n int, g1, g2 []byte, gtSize int, flags uint32) []byte {
+	out := make([]byte, n*gtSize)
+	check("pairing", C.b200_pairing_batch(C.int(curve), C.size_t(n), ptr(g1), ptr(g2), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func pairing2Batch(curve int, n int, g1a, g2a, g1b, g2b []byte, gtSize int, flags uint32) []byte {
+	out := make([]byte, n*gtSize)
+	check("pairing 2", C.b200_pairing2_batch(C.int(curve), C.size_t(n), ptr(g1a), ptr(g2a), ptr(g1b), ptr(g2b), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func fexpBatch(curve int, n int, gt []byte, flags uint32) []byte {
+	out := make([]byte, len(gt))
+	check("final exponentiation", C.b200_fexp_batch(C.int(curve), C.size_t(n), ptr(gt), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func g1MulBatch(curve int, n int, pts, scalars []byte, flags uint32) []byte {
+	out := make([]byte, len(pts))
+	check("g1 mul", C.b200_g1_mul_batch(C.int(curve), C.size_t(n), ptr(pts), ptr(scalars), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func g1Mul2Batch(curve int, n int, p, e, q, f []byte, flags uint32) []byte {
+	out := make([]byte, len(p))
+	check("g1 mul2", C.b200_g1_mul2_batch(C.int(curve), C.size_t(n), ptr(p), ptr(e), ptr(q), ptr(f), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func g1Msm(curve int, n int, pts, scalars []byte, g1Size int, flags uint32) []byte {
+	out := make([]byte, g1Size)
+	check("multi scalar mul", C.b200_g1_msm(C.int(curve), C.size_t(n), ptr(pts), ptr(scalars), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func g1Sum(curve int, n int, pts []byte, g1Size int) []byte {
+	out := make([]byte, g1Size)
+	check("g1 sum", C.b200_g1_sum(C.int(curve), C.size_t(n), ptr(pts), ptr(out), 0))
+	return out
+}

@@ -259,6 +259,85 @@ struct FpOps {
         reduce_once(r);
     }
     static B200_HD void sqr(E& r, const E& a) { mul(r, a, a); }
+    // Multi-operand Montgomery product ("Montgomery dot product"):  r = (sum_{t<T} a[t]*b[t]) / R  mod p, fully reduced.
+    // Same row structure as mul(): per row the T multiplicand chains accumulate into the SAME even/odd accumulators and
+    // ONE reduction row follows, so T products cost T*N^2 + N^2 + N multiply-accumulates instead of T*(2N^2+N) --
+    // the lazy reduction of the pairing VM without any wide (2N-word) arithmetic.  Requires T <= 3 (top-limb headroom:
+    // (T+1) * 2^30 <= 2^32 in the odd accumulator) and canonical inputs; the unreduced result is < (T*p/R + 1) p < 2p.
+    template <int T>
+    static B200_HD void mul_dot(E& r, const E* a, const E* b) {
+        static_assert(T >= 1 && T <= 3, "mul_dot: 1..3 operands");
+        const uint32_t* p = C::p();
+        uint32_t X[N + 2], Y[N + 2];
+        // row 0
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            X[j] = mul_lo(a[0].l[j], b[0].l[0]);
+            X[j + 1] = mul_hi(a[0].l[j], b[0].l[0]);
+            Y[j] = mul_lo(a[0].l[j + 1], b[0].l[0]);
+            Y[j + 1] = mul_hi(a[0].l[j + 1], b[0].l[0]);
+        }
+        X[N] = 0; X[N + 1] = 0; Y[N] = 0; Y[N + 1] = 0;
+#pragma unroll
+        for (int t = 1; t < T; t++) {
+            chain_odd(Y, a[t].l, b[t].l[0]);
+            chain_even(X, a[t].l, b[t].l[0]);
+            X[N] = addc(X[N], 0);
+        }
+        {
+            uint32_t m = mul_lo(X[0], C::inv32());
+            chain_odd(Y, p, m);
+            chain_even(X, p, m);
+            X[N] = addc(X[N], 0);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i += 2) {
+            row_dot<T>(X, Y, a, b, i);
+            if (i + 1 < N) row_dot<T>(Y, X, a, b, i + 1);
+        }
+        r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(X[i], Y[i + 1]);
+        r.l[N - 1] = addc(X[N - 1], Y[N]);
+        reduce_once(r);
+    }
+    // register-operand front ends (arrays of operands get demoted to local memory by the compiler)
+    static B200_HD void mul_dot2(E& r, const E& a0, const E& b0, const E& a1, const E& b1) {
+        const E a[2] = {a0, a1}, b[2] = {b0, b1};
+        mul_dot<2>(r, a, b);
+    }
+    static B200_HD void mul_dot3(E& r, const E& a0, const E& b0, const E& a1, const E& b1, const E& a2, const E& b2) {
+        const E a[3] = {a0, a1, a2}, b[3] = {b0, b1, b2};
+        mul_dot<3>(r, a, b);
+    }
+    // one row of mul_dot: A = previous even accumulator (A[0] == 0, stray A[1], carry word A[N]), B = previous odd one
+    template <int T>
+    static B200_HD void row_dot(uint32_t* A, uint32_t* B, const E* a, const E* b, int i) {
+        const uint32_t* p = C::p();
+        const uint32_t b0 = b[0].l[i];
+        B[0] = add_cc(B[0], A[1]);
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) {
+            A[j] = madc_lo_cc(a[0].l[j + 1], b0, A[j + 2]);
+            A[j + 1] = madc_hi_cc(a[0].l[j + 1], b0, A[j + 3]);
+        }
+        A[N - 2] = madc_lo_cc(a[0].l[N - 1], b0, A[N]);
+        A[N - 1] = madc_hi(a[0].l[N - 1], b0, 0);
+        chain_even(B, a[0].l, b0);
+        B[N] = addc(0, 0);
+#pragma unroll
+        for (int t = 1; t < T; t++) {
+            const uint32_t bt = b[t].l[i];
+            chain_odd(A, a[t].l, bt);
+            chain_even(B, a[t].l, bt);
+            B[N] = addc(B[N], 0);
+        }
+        uint32_t m = mul_lo(B[0], C::inv32());
+        chain_odd(A, p, m);
+        chain_even(B, p, m);
+        B[N] = addc(B[N], 0);
+    }
+
     // out-of-line product for callers whose hot loop must stay inside the instruction cache (G1 point formulas)
     static B200_HD_NOINLINE void mulx(E& r, const E& a, const E& b) { mul(r, a, b); }
     static B200_HD void sqrx(E& r, const E& a) { mulx(r, a, a); }

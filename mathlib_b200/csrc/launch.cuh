@@ -93,7 +93,9 @@ struct Launch {
         cudaError_t e;
         int dev = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        const size_t smem = vm_smem_bytes<C>();
+        // experiment: B200_VM_ONEBLOCK=1 pads the shared-memory request so that only one block fits per SM
+        static int oneblock = getenv("B200_VM_ONEBLOCK") ? atoi(getenv("B200_VM_ONEBLOCK")) : 0;
+        const size_t smem = oneblock ? (size_t)120 * 1024 : vm_smem_bytes<C>();
         if (cfg_dev != dev) {
             // per device: upload the microcode once and opt in to the large dynamic shared memory carve-out
             static std::mutex mu;

@@ -259,7 +259,7 @@ struct VmDriver {
 };
 
 #if defined(__CUDACC__)
-#define B200_VM_WARPS 8
+#define B200_VM_WARPS 4
 #define B200_VM_GROUPS_PER_WARP 5
 #define B200_VM_GROUP_PAD 4          // words; staggers the groups across shared-memory banks
 
@@ -272,7 +272,7 @@ __host__ __device__ constexpr size_t vm_smem_bytes() {
 }
 
 template <class C, int NP>
-__global__ void __launch_bounds__(B200_VM_WARPS * 32, 1)
+__global__ void __launch_bounds__(B200_VM_WARPS * 32, 2)
 vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
                   uint8_t* out, uint32_t flags, int* err, const uint32_t* mc_words, const VmDirEntry* mc_dir) {
     extern __shared__ uint32_t smem[];

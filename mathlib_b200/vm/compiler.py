@@ -260,6 +260,9 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
     words = []
     for kind, vs in phases:
         lanes = list(vs) + [None] * (G - len(vs))
+        # the widest dot product of the phase: every lane runs the same multi-operand product variant (zero padded),
+        # so lanes with fewer terms do not serialise against the others
+        pmax = max([len(v.terms) for v in vs if v.kind == 'dot'] + [0])
         for v in lanes:
             w = [0] * OP_WORDS
             if v is not None:
@@ -268,7 +271,8 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
                 nl = len(v.lin)
                 alt = enc_operand(loc(v.alt)) if v.alt is not None else 0
                 assert 1 <= v.scale <= 7
-                w[0] = k | (nt << 4) | (nl << 8) | (v.scale << 12) | ((1 if v.halve else 0) << 15) | (v.pred << 16)
+                w[0] = (k | (nt << 4) | (nl << 8) | (v.scale << 12) | ((1 if v.halve else 0) << 15) | (v.pred << 16) |
+                        (pmax << 20))
                 w[1] = enc_operand(loc(v)) | (alt << 16)
                 for t, (a, am, b, bm) in enumerate(v.terms):
                     w[2 + t] = enc_operand(loc(a)) | (enc_operand(loc(b)) << 11) | (am << 22) | (bm << 26)

@@ -156,3 +156,16 @@ extern "C" int he_vm_pairing(int curve, int np, const uint8_t* g1a, const uint8_
     if (curve == 1) return t_vm_pair<BLS381>(np, g1a, g2a, g1b, g2b, out, fexp);
     return t_vm_pair<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
 }
+
+// mul_dot<T>: r = sum a[t]*b[t] / R mod p  (operands as 3 consecutive Fp each)
+template <class C> static void t_dot(int T, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    typedef FpOps<C> F; typename F::E x[3], y[3], z;
+    for (int t = 0; t < 3; t++) for (int i = 0; i < C::N; i++) { x[t].l[i] = a[t * C::N + i]; y[t].l[i] = b[t * C::N + i]; }
+    if (T == 1) F::template mul_dot<1>(z, x, y); else if (T == 2) F::template mul_dot<2>(z, x, y); else F::template mul_dot<3>(z, x, y);
+    for (int i = 0; i < C::N; i++) o[i] = z.l[i];
+}
+extern "C" void he_fp_dot(int curve, int T, const uint32_t* a, const uint32_t* b, uint32_t* o) {
+    if (curve == 0) t_dot<BN254>(T, a, b, o);
+    else if (curve == 1) t_dot<BLS381>(T, a, b, o);
+    else t_dot<BLS377>(T, a, b, o);
+}

@@ -247,6 +247,17 @@ struct VmDriver {
             else CD::fp_to_bytes(out + (11 - e) * C::FP_BYTES, v);
         }
     }
+    // lane r loads w-basis coefficient r (2 Fp) of a Gt element into the Fp12 register at slot base fb
+    B200_HD void load_coeff(int r, uint32_t fb, const uint8_t* in, bool mont, int* err) {
+        uint32_t* dst = ctx.slots + (fb + r) * SW;
+        for (int a = 0; a < 2; a++) {
+            Fp<N> v;
+            int e = ((r & 1) * 3 + (r >> 1)) * 2 + a;
+            if (mont) CD::fp_from_mont_words(v, (const uint32_t*)in + e * N);
+            else CD::fp_from_bytes(v, in + (11 - e) * C::FP_BYTES, 0xFF, err);
+            for (int i = 0; i < N; i++) dst[a * N + i] = v.l[i];
+        }
+    }
     B200_HD bool coeff_is_one_part(int r, uint32_t fb) {
         const uint32_t* src = ctx.slots + (fb + r) * SW;
         uint32_t d = 0;
@@ -325,6 +336,54 @@ vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_
     if (flags & FLAG_UNITY) {
         const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
+    } else if (active) {
+        D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+    }
+}
+// standalone driver.Curve.FExp on the VM (same slot file / microcode as the pairing kernel)
+template <class C>
+__global__ void __launch_bounds__(B200_VM_WARPS * 32, 2)
+vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, const uint32_t* mc_words,
+               const VmDirEntry* mc_dir) {
+    extern __shared__ uint32_t smem[];
+    constexpr int N = C::N;
+    constexpr int GPB = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
+    uint32_t* s_slots = smem;
+    uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
+    uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
+    if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = lane / VM_G;
+    const int role = gw < B200_VM_GROUPS_PER_WARP ? lane % VM_G : -1;
+    const int gblock = warp * B200_VM_GROUPS_PER_WARP + (gw < B200_VM_GROUPS_PER_WARP ? gw : 0);
+    const size_t item = (size_t)blockIdx.x * GPB + gblock;
+    const bool active = role >= 0 && item < n;
+    VmDriver<C> D;
+    D.ctx.slots = s_slots + (size_t)gblock * vm_group_stride<C>();
+    D.ctx.kbank = s_kbank;
+    D.ctx.live = 3;
+    D.words = s_words;
+    D.dir = s_dir;
+    D.role = active ? role : -1;
+    typedef Codec<C> CD;
+    int e = 0;
+    if (active) D.load_coeff(role, 0, in + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
+    if (__ballot_sync(0xffffffffu, e != 0)) {
+        if (lane == 0) atomicExch(err, 1);
+        return;
+    }
+    __syncwarp();
+    uint32_t fb = 0;
+    if (flags & FLAG_FEXP) fb = D.final_exp(0);
+    if (flags & FLAG_UNITY) {
+        const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
         if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
     } else if (active) {
         D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);

@@ -207,6 +207,8 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
     b->counts = (uint32_t*)take(nb * 4);
     b->offsets = (uint32_t*)take(nb * 4);
     b->cursor = (uint32_t*)take(nb * 4);
+    b->perm = (uint32_t*)take(nb * 4);
+    b->size_hist = (uint32_t*)take(2 * 1024 * 4);
     b->buckets = take(nb * vt->xyzz_size);
     b->chunks = take((size_t)pl.W * pl.nchunks * vt->xyzz_size);
     b->windows = take((size_t)pl.W * vt->xyzz_size);

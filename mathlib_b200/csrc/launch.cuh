@@ -21,6 +21,8 @@ struct MsmBuffers {            // device pointers carved out of one workspace sl
     uint32_t* counts;          // W * B
     uint32_t* offsets;         // W * B
     uint32_t* cursor;          // W * B
+    uint32_t* perm;            // W * B   bucket ids by decreasing size
+    uint32_t* size_hist;       // 2 * B200_MSM_SIZE_BINS (histogram, start offsets)
     void* buckets;             // W * B * sizeof(G1XYZZ)
     void* chunks;              // W * nchunks * sizeof(G1XYZZ)
     void* windows;             // W * sizeof(G1XYZZ)
@@ -208,8 +210,13 @@ struct Launch {
             msm_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, pl, b.digits, b.cursor, b.sorted);
             B200_COUNT_LAUNCH();
         }
+        if ((e = cudaMemsetAsync(b.size_hist, 0, 2 * B200_MSM_SIZE_BINS * sizeof(uint32_t), s)) != cudaSuccess) return e;
+        msm_size_hist_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist);
+        msm_size_scan_kernel<<<1, B200_MSM_SIZE_BINS, 0, s>>>(b.size_hist, b.size_hist + B200_MSM_SIZE_BINS);
+        msm_size_scatter_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist + B200_MSM_SIZE_BINS, b.perm);
+        B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
         msm_accumulate_kernel<C><<<blocks_for(nb, 128), 128, 0, s>>>(n, pl, (const G1Affine<C::N>*)pts, b.offsets,
-                                                                    b.counts, b.sorted, (Pt*)b.buckets);
+                                                                    b.counts, b.sorted, b.perm, (Pt*)b.buckets);
         B200_COUNT_LAUNCH();
         msm_reduce_kernel<C><<<blocks_for((size_t)pl.W * pl.nchunks, 128), 128, 0, s>>>(pl, (const Pt*)b.buckets,
                                                                                         (Pt*)b.chunks);

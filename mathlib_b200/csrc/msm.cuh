@@ -35,7 +35,7 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
     p.c = c;
     p.W = scalar_bits / c + 1;
     p.B = 1 << (c - 1);
-    p.chunk = p.B >= 1024 ? 32 : (p.B >= 32 ? 8 : 1);
+    p.chunk = p.B >= 1024 ? 16 : (p.B >= 32 ? 8 : 1);
     p.nchunks = p.B / p.chunk;
     return p;
 }
@@ -129,12 +129,45 @@ static __global__ void msm_scatter_kernel(size_t n, MsmPlan pl, const uint32_t* 
     }
 }
 
+// Load balancing: buckets are handed to threads in order of decreasing size (counting sort of the bucket ids by
+// their point count, sizes clamped to 1023), so the 32 threads of a warp run the same number of mixed additions.
+#define B200_MSM_SIZE_BINS 1024
+static __global__ void msm_size_hist_kernel(size_t nb, const uint32_t* counts, uint32_t* hist) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    uint32_t c = counts[t];
+    atomicAdd(&hist[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
+}
+// exclusive scan of hist in DESCENDING size order -> start[]; single block of B200_MSM_SIZE_BINS threads
+static __global__ void msm_size_scan_kernel(const uint32_t* hist, uint32_t* start) {
+    __shared__ uint32_t sh[B200_MSM_SIZE_BINS];
+    int i = threadIdx.x;                         // rank 0 = largest size
+    uint32_t v = hist[B200_MSM_SIZE_BINS - 1 - i];
+    sh[i] = v;
+    __syncthreads();
+    for (int d = 1; d < B200_MSM_SIZE_BINS; d <<= 1) {
+        uint32_t x = i >= d ? sh[i - d] : 0;
+        __syncthreads();
+        sh[i] += x;
+        __syncthreads();
+    }
+    start[B200_MSM_SIZE_BINS - 1 - i] = sh[i] - v;
+}
+static __global__ void msm_size_scatter_kernel(size_t nb, const uint32_t* counts, uint32_t* start, uint32_t* perm) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    uint32_t c = counts[t];
+    uint32_t pos = atomicAdd(&start[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
+    perm[pos] = (uint32_t)t;
+}
+
 template <class C>
 __global__ void __launch_bounds__(128, 2)
 msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
-                      const uint32_t* sorted, G1XYZZ<C::N>* buckets) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)pl.W * pl.B) return;
+                      const uint32_t* sorted, const uint32_t* perm, G1XYZZ<C::N>* buckets) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)pl.W * pl.B) return;
+    const size_t t = perm[tid];
     typedef G1Ops<C> G;
     size_t w = t / pl.B;
     const uint32_t* run = sorted + w * n + offsets[t];
@@ -213,15 +246,62 @@ __global__ void msm_window_sum_kernel(MsmPlan pl, const G1XYZZ<C::N>* chunk_in, 
     if (threadIdx.x == 0) window_out[w] = sh[0];
 }
 
-// Horner over windows, then affine + store. Single thread.
+// Horner over the windows, then affine normalisation + store.  One thread: this is a pure dependency chain of
+// c*(W-1) doublings, so it is written for latency -- Jacobian doubling (2M+5S) with the Fp products inlined so the
+// independent ones overlap in the pipe, instead of the out-of-line XYZZ formulas.
+template <class C>
+struct JacOps {
+    typedef FpOps<C> F;
+    typedef Fp<C::N> E;
+    struct Pt { E x, y, z; };          // z == 0 <=> infinity
+    static __device__ __forceinline__ void dbl(Pt& p) {          // dbl-2009-l, a = 0
+        E A, B, Cc, D, Ev, Fv, t;
+        F::sqr(A, p.x);
+        F::sqr(B, p.y);
+        F::mul(t, p.y, p.z);
+        F::sqr(Cc, B);
+        F::add(D, p.x, B);
+        F::sqr(D, D);
+        F::sub(D, D, A); F::sub(D, D, Cc); F::dbl(D, D);
+        F::dbl(Ev, A); F::add(Ev, Ev, A);
+        F::sqr(Fv, Ev);
+        F::dbl(p.z, t);
+        F::sub(p.x, Fv, D); F::sub(p.x, p.x, D);
+        F::sub(t, D, p.x);
+        F::mul(t, Ev, t);
+        F::dbl(Cc, Cc); F::dbl(Cc, Cc); F::dbl(Cc, Cc);
+        F::sub(p.y, t, Cc);
+    }
+};
+
 template <class C>
 __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_t* out, uint32_t flags) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     typedef G1Ops<C> G;
+    typedef FpOps<C> F;
+    typedef JacOps<C> J;
     typename G::Pt acc;
     G::set_inf(acc);
     for (int w = pl.W - 1; w >= 0; w--) {
-        for (int k = 0; k < pl.c; k++) G::dbl(acc);
+        if (!G::is_inf(acc)) {
+            // XYZZ (X, Y, ZZ, ZZZ) -> Jacobian with Z = ZZZ/ZZ would need an inversion; use the equivalent
+            // representative (X*ZZ^2... ) : scale to Z' = ZZ*ZZZ:  x = X/ZZ = (X*ZZ*ZZZ^2)/Z'^2, y = Y/ZZZ = (Y*ZZ^3*ZZZ^2)/Z'^3
+            typename J::Pt j;
+            typename F::E zz2, zzz2, t;
+            F::sqr(zzz2, acc.zzz);
+            F::sqr(zz2, acc.zz);
+            F::mul(t, acc.x, acc.zz);
+            F::mul(j.x, t, zzz2);
+            F::mul(t, acc.y, zz2);
+            F::mul(t, t, acc.zz);
+            F::mul(j.y, t, zzz2);
+            F::mul(j.z, acc.zz, acc.zzz);
+            for (int k = 0; k < pl.c; k++) J::dbl(j);
+            // back to XYZZ: ZZ = Z^2, ZZZ = Z^3
+            acc.x = j.x; acc.y = j.y;
+            F::sqr(acc.zz, j.z);
+            F::mul(acc.zzz, acc.zz, j.z);
+        }
         typename G::Pt v = windows[w];
         G::add(acc, v);
     }

@@ -7,7 +7,7 @@ CXX ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 CSRC := mathlib_b200/csrc
-HDRS := $(wildcard $(CSRC)/*.cuh) $(CSRC)/constants.h include/b200.h
+HDRS := $(wildcard $(CSRC)/*.cuh) $(CSRC)/constants.h $(CSRC)/microcode.h include/b200.h
 OBJS := $(CSRC)/build/abi.o $(CSRC)/build/kernels_bn254.o $(CSRC)/build/kernels_bls381.o $(CSRC)/build/kernels_bls377.o
 
 .PHONY: all lib hostemu oracle clean

@@ -67,16 +67,16 @@ struct VmDriver {
         __syncwarp();
 #endif
     }
-    B200_HD_NOINLINE void run(int prog, uint32_t b1, uint32_t b2, uint32_t b3) {
+    B200_HD void run(int prog, uint32_t b1, uint32_t b2, uint32_t b3) {
         ctx.base[0] = b1; ctx.base[1] = b2; ctx.base[2] = b3;
         const uint32_t* w = words + dir[prog].offset;
         const uint32_t nph = dir[prog].phases;
         for (uint32_t ph = 0; ph < nph; ph++) {
 #if defined(__CUDA_ARCH__)
-            if (role >= 0) M::exec_op(ctx, w + (ph * VM_G + role) * VM_OP_WORDS);
+            if (role >= 0) M::exec_op(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, w + (ph * VM_G + role) * VM_OP_WORDS);
             __syncwarp();
 #else
-            for (int r = 0; r < VM_G; r++) M::exec_op(ctx, w + (ph * VM_G + r) * VM_OP_WORDS);
+            for (int r = 0; r < VM_G; r++) M::exec_op(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, w + (ph * VM_G + r) * VM_OP_WORDS);
 #endif
         }
     }

@@ -38,7 +38,8 @@ struct Vm {
     static B200_HD const uint32_t* operand_ptr(const Ctx& c, uint32_t o) {
         uint32_t cls = (o >> 8) & 7, idx = o & 255;
         if (cls == VM_C_CONST) return c.kbank + idx * SLOT_WORDS;
-        uint32_t b = cls == VM_C_ABS ? 0u : c.base[cls - 1];
+        // no dynamic indexing of base[] (it would force the context into local memory)
+        uint32_t b = cls == VM_C_ABS ? 0u : (cls == VM_C_B1 ? c.base[0] : (cls == VM_C_B2 ? c.base[1] : c.base[2]));
         return c.slots + (b + idx) * SLOT_WORDS;
     }
     // slots are 16-byte aligned (slot = 2N words, N a multiple of 4): 128-bit accesses
@@ -220,7 +221,10 @@ struct Vm {
     // ---------------------------------------------------------------------------------------------------
     // one op
     // ---------------------------------------------------------------------------------------------------
-    static B200_HD_NOINLINE void exec_op(const Ctx& c, const uint32_t* w) {
+    static B200_HD_NOINLINE void exec_op(uint32_t* slots, const uint32_t* kbank, uint32_t b1, uint32_t b2, uint32_t b3,
+                                         uint32_t live, const uint32_t* w) {
+        Ctx c;
+        c.slots = slots; c.kbank = kbank; c.base[0] = b1; c.base[1] = b2; c.base[2] = b3; c.live = live;
         const uint32_t hdr = w[0];
         const uint32_t kind = hdr & 15;
         if (kind == VM_NOP) return;

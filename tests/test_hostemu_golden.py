@@ -62,3 +62,47 @@ def test_bad_encoding_flag(hostemu):
     out = ctypes.create_string_buffer(96)
     bad = b"\x1f" + b"\xff" * 95
     assert hostemu.he_g1_op(1, 0, bad, (1).to_bytes(32, "big"), None, None, out) == 1
+
+
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_vm_pairing(hostemu, cid):
+    """the warp-cooperative VM interpreter (vm.cuh + pairing_vm.cuh + microcode.h) on the host: lanes of a phase run
+    one after another; raw Miller value and final exponentiation against the golden vectors."""
+    v = load_vectors(cid)
+    ec = EMU_CURVE[cid]
+    n = 32 if cid == 1 else 48
+    out = ctypes.create_string_buffer(12 * n)
+    for case in v["pairing"]:
+        assert hostemu.he_vm_pairing(ec, 1, bytes.fromhex(case["g1"]), bytes.fromhex(case["g2"]), None, None, out, 0) == 0
+        assert out.raw.hex() == case["pairing"]
+        assert hostemu.he_vm_pairing(ec, 1, bytes.fromhex(case["g1"]), bytes.fromhex(case["g2"]), None, None, out, 1) == 0
+        assert out.raw.hex() == case["canonical"]
+    for case in v["pairing2"]:
+        args = [bytes.fromhex(case[k]) for k in ("g1a", "g2a", "g1b", "g2b")]
+        assert hostemu.he_vm_pairing(ec, 2, *args, out, 0) == 0 and out.raw.hex() == case["pairing2"]
+        assert hostemu.he_vm_pairing(ec, 2, *args, out, 1) == 0 and out.raw.hex() == case["fexp"]
+
+
+def test_fp_inverse_and_dot(hostemu):
+    """binary extended-Euclid inversion == Fermat; multi-operand Montgomery product == sum of products."""
+    import random
+    from oracle.params import BN254, BLS12_381, BLS12_377
+    rnd = random.Random(17)
+    for ci, P in enumerate([BN254, BLS12_381, BLS12_377]):
+        n = P.limbs32
+        R = 1 << (32 * n)
+        arr = lambda vs: (ctypes.c_uint32 * (len(vs) * n))(*[(v >> (32 * i)) & 0xFFFFFFFF for v in vs for i in range(n)])
+        val = lambda o: sum(int(x) << (32 * i) for i, x in enumerate(o))
+        for a in [1, P.p - 1, 0] + [rnd.randrange(1, P.p) for _ in range(40)]:
+            o, o2 = (ctypes.c_uint32 * n)(), (ctypes.c_uint32 * n)()
+            hostemu.he_fp_op(ci, 5, arr([a]), arr([0]), o)
+            hostemu.he_fp_op(ci, 8, arr([a]), arr([0]), o2)
+            want = 0 if a == 0 else pow(a * pow(R, -1, P.p) % P.p, -1, P.p) * R % P.p
+            assert val(o) == want == val(o2)
+        for _ in range(60):
+            a = [rnd.randrange(P.p) for _ in range(3)]
+            b = [rnd.randrange(P.p) for _ in range(3)]
+            for T in (1, 2, 3):
+                o = (ctypes.c_uint32 * n)()
+                hostemu.he_fp_dot(ci, T, arr(a), arr(b), o)
+                assert val(o) == sum(a[t] * b[t] for t in range(T)) * pow(R, -1, P.p) % P.p

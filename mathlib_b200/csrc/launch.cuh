@@ -59,6 +59,11 @@ static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned
 
 template <class C>
 struct Launch {
+    // development knob: unused dynamic shared memory caps the resident blocks of the G1 kernels (measured: no gain)
+    static size_t g1_smem_pad() {
+        static long v = getenv("B200_G1_SMEM_PAD") ? atol(getenv("B200_G1_SMEM_PAD")) : 0;
+        return (size_t)v;
+    }
     static bool legacy_for_bn() {
         static int off = getenv("B200_BN_VM") ? atoi(getenv("B200_BN_VM")) : 0;
         return !off;
@@ -169,14 +174,14 @@ struct Launch {
     static cudaError_t g1_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
                               cudaStream_t s) {
         if (n == 0) return cudaSuccess;
-        g1_mul_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, 0, s>>>(n, pts, k, out, flags, err);
+        g1_mul_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, g1_smem_pad(), s>>>(n, pts, k, out, flags, err);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
     static cudaError_t g1_mul2(size_t n, const uint8_t* P, const uint8_t* e, const uint8_t* Q, const uint8_t* f,
                                uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
         if (n == 0) return cudaSuccess;
-        g1_mul2_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, 0, s>>>(n, P, e, Q, f, out, flags, err);
+        g1_mul2_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, g1_smem_pad(), s>>>(n, P, e, Q, f, out, flags, err);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }

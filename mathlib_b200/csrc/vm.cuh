@@ -74,33 +74,30 @@ struct Vm {
     // wide arithmetic
     // ---------------------------------------------------------------------------------------------------
     static constexpr int AW = 2 * N + 2;         // words of an even / odd accumulator array
-    // Product-scanning multiply-accumulate of up to three independent wide accumulators in lock-step:
-    //   X += a0*b0,  Y += a1*b1 (skipped when !with_y),  Z += sa*sb          (all unreduced, W words each)
+    // Product-scanning multiply-accumulate of one or two independent wide accumulators in lock-step:
+    //   X += a0*b0  [and  Y += a1*b1]          (unreduced, W words each)
     // Column k collects the products a[i]*b[k-i] in a 96-bit running sum (c0,c1,c2): one IMAD.WIDE.U32 (carry out)
-    // plus one IADD3.X per product.  Each accumulator is one dependent chain; running the three side by side gives
-    // the FMA-heavy pipe three independent chains per warp and needs no temporary product arrays.
-    static B200_HD void wide_mac3(uint32_t* X, uint32_t* Y, uint32_t* Z, const uint32_t* a0, const uint32_t* b0,
-                                  const uint32_t* a1, const uint32_t* b1, const uint32_t* sa, const uint32_t* sb,
-                                  bool with_y) {
+    // plus one IADD3.X per product.  Each accumulator is one dependent chain.  The Karatsuba cross term is accumulated
+    // in a second call so that the register footprint stays below 168 (12 resident warps per SM).
+    template <bool TWO>
+    static B200_HD void wide_mac2(uint32_t* X, uint32_t* Y, const uint32_t* a0, const uint32_t* b0, const uint32_t* a1,
+                                  const uint32_t* b1) {
         uint32_t x0 = X[0], x1 = X[1], x2 = 0;
-        uint32_t y0 = Y[0], y1 = Y[1], y2 = 0;
-        uint32_t z0 = Z[0], z1 = Z[1], z2 = 0;
+        uint32_t y0 = 0, y1 = 0, y2 = 0;
+        if (TWO) { y0 = Y[0]; y1 = Y[1]; }
 #pragma unroll
         for (int k = 0; k < 2 * N - 1; k++) {
 #pragma unroll
             for (int i = (k < N ? 0 : k - N + 1); i <= (k < N ? k : N - 1); i++) {
                 const int j = k - i;
                 x0 = mad_lo_cc(a0[i], b0[j], x0); x1 = madc_hi_cc(a0[i], b0[j], x1); x2 = addc(x2, 0);
-                if (with_y) { y0 = mad_lo_cc(a1[i], b1[j], y0); y1 = madc_hi_cc(a1[i], b1[j], y1); y2 = addc(y2, 0); }
-                z0 = mad_lo_cc(sa[i], sb[j], z0); z1 = madc_hi_cc(sa[i], sb[j], z1); z2 = addc(z2, 0);
+                if (TWO) { y0 = mad_lo_cc(a1[i], b1[j], y0); y1 = madc_hi_cc(a1[i], b1[j], y1); y2 = addc(y2, 0); }
             }
             X[k] = x0; x0 = x1; x1 = add_cc(x2, X[k + 2]); x2 = addc(0, 0);
-            if (with_y) { Y[k] = y0; y0 = y1; y1 = add_cc(y2, Y[k + 2]); y2 = addc(0, 0); }
-            Z[k] = z0; z0 = z1; z1 = add_cc(z2, Z[k + 2]); z2 = addc(0, 0);
+            if (TWO) { Y[k] = y0; y0 = y1; y1 = add_cc(y2, Y[k + 2]); y2 = addc(0, 0); }
         }
         X[2 * N - 1] = x0; X[2 * N] = x1;
-        if (with_y) { Y[2 * N - 1] = y0; Y[2 * N] = y1; }
-        Z[2 * N - 1] = z0; Z[2 * N] = z1;
+        if (TWO) { Y[2 * N - 1] = y0; Y[2 * N] = y1; }
     }
     // v[0..W) = Ev + (Od << 32)
     static B200_HD void wide_merge(uint32_t* v, const uint32_t* Ev, const uint32_t* Od) {
@@ -265,16 +262,17 @@ struct Vm {
                 } else if (bm & 3) {
                     apply_mod(b, bm & 3);
                 }
-                // sums (a0+a1), (b0+b1) stay below 2p < 2^(32N); for a real b this is (a0+a1) * s
-                uint32_t sa[N], sb[N];
-                sa[0] = add_cc(a.c0.l[0], a.c1.l[0]);
+                if (real_b) wide_mac2<false>(Xm, Ym, a.c0.l, b.c0.l, a.c1.l, b.c1.l);
+                else wide_mac2<true>(Xm, Ym, a.c0.l, b.c0.l, a.c1.l, b.c1.l);
+                // sums (a0+a1), (b0+b1) stay below 2p < 2^(32N); for a real b this is (a0+a1) * s.  Formed in place:
+                // the halves are dead after the X / Y products
+                a.c0.l[0] = add_cc(a.c0.l[0], a.c1.l[0]);
 #pragma unroll
-                for (int i = 1; i < N; i++) sa[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
-                sb[0] = add_cc(b.c0.l[0], b.c1.l[0]);
+                for (int i = 1; i < N; i++) a.c0.l[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
+                b.c0.l[0] = add_cc(b.c0.l[0], b.c1.l[0]);
 #pragma unroll
-                for (int i = 1; i < N; i++) sb[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
-                if (real_b) wide_mac3(Xm, Ym, IM, a.c0.l, b.c0.l, a.c1.l, b.c1.l, sa, sb, false);
-                else wide_mac3(Xm, Ym, IM, a.c0.l, b.c0.l, a.c1.l, b.c1.l, sa, sb, true);
+                for (int i = 1; i < N; i++) b.c0.l[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
+                wide_mac2<false>(IM, IM, a.c0.l, b.c0.l, a.c0.l, b.c0.l);
             }
             uint32_t RE[W];
             {

@@ -120,3 +120,90 @@ def test_multi_gpu_split_matches_single(m):
     m.check(lib.b200_set_device(0))
     single = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP)
     assert multi == single
+
+
+def test_resident_bases_and_threads(m):
+    """b200_bases_upload / b200_g1_msm_resident against the one-shot MSM, and concurrent calls from several host
+    threads sharing read-only inputs (the reference benchmarks call one curve from many goroutines, perf_test.go:392-405)."""
+    import ctypes
+    import threading
+    lib = m.load()
+    c = m.Curves[5]
+    n = 5000
+    g1a, g2a, g1b, g2b, expect = rand_inputs(m, 5, n, seed=91)
+    rnd = random.Random(4)
+    ks = b"".join(rnd.randrange(c.order).to_bytes(32, "big") for _ in range(n))
+    want = c.MsmBatch(g1a, ks, n)
+    h = ctypes.c_uint64()
+    m.check(lib.b200_bases_upload(5, n, m.buf_ptr(g1a), 0, ctypes.byref(h)))
+    out = ctypes.create_string_buffer(c.G1ByteSize)
+    m.check(lib.b200_g1_msm_resident(h.value, n, m.buf_ptr(ks), out, 0))
+    assert out.raw == want
+    m.check(lib.b200_g1_msm_resident(h.value, 100, m.buf_ptr(ks), out, 0))          # prefix of the bases
+    assert out.raw == c.MsmBatch(g1a[:100 * c.G1ByteSize], ks[:100 * 32], 100)
+    m.check(lib.b200_bases_free(h.value))
+    with pytest.raises(m.B200Error):
+        m.check(lib.b200_g1_msm_resident(h.value, n, m.buf_ptr(ks), out, 0))
+    # concurrency
+    ref = c.Pairing2Batch(g1a, g2a, g1b, g2b, 512, m.FEXP | m.OUT_UNITY_ONLY)
+    results, errors = [None] * 6, []
+
+    def worker(i):
+        try:
+            if i % 2:
+                results[i] = c.Pairing2Batch(g1a, g2a, g1b, g2b, 512, m.FEXP | m.OUT_UNITY_ONLY)
+            else:
+                results[i] = c.MsmBatch(g1a, ks, n)
+        except Exception as ex:       # noqa: BLE001
+            errors.append(ex)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors
+    for i in range(6):
+        assert results[i] == (ref if i % 2 else want)
+
+
+def test_mont_slabs_for_pairing(m):
+    """IN_MONT / OUT_MONT: the zero-conversion path for gnark-layout slabs gives the same values as BYTES."""
+    import ctypes
+    lib = m.load()
+    c = m.Curves[5]
+    n = 64
+    g1a, g2a, g1b, g2b, _ = rand_inputs(m, 5, n, seed=12)
+    raw_b = c.Pairing2Batch(g1a, g2a, g1b, g2b, n)
+    raw_m = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.OUT_MONT)
+    assert c.FExpBatch(raw_m, n, m.IN_MONT) == c.FExpBatch(raw_b, n)
+    # G1 to Montgomery slabs via [1]P, then pairing with IN_MONT for G1 is not mixed-format capable: check G1 Mul only
+    one = (1).to_bytes(32, "big") * n
+    pm = ctypes.create_string_buffer(n * c.G1ByteSize)
+    m.check(lib.b200_g1_mul_batch(5, n, m.buf_ptr(g1a), m.buf_ptr(one), pm, m.OUT_MONT))
+    back = ctypes.create_string_buffer(n * c.G1ByteSize)
+    m.check(lib.b200_g1_mul_batch(5, n, pm, m.buf_ptr(one), back, m.IN_MONT))
+    assert back.raw == g1a
+
+
+def test_multi_gpu_msm_matches_single(m):
+    lib = m.load()
+    if lib.b200_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c = m.Curves[5]
+    n = 1 << 17
+    g1a, _, _, _, _ = rand_inputs(m, 5, 4096, seed=5)
+    pts = g1a * (n // 4096)
+    rnd = np.random.default_rng(3)
+    ks = rnd.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks[:, 0] &= 0x3F
+    lib2 = m.load()
+    import mathlib_b200._lib as L
+    # fresh thread: device not pinned -> range split over all GPUs + partial-sum combine
+    import threading
+    res = {}
+    t = threading.Thread(target=lambda: res.setdefault("multi", c.MsmBatch(pts, ks.tobytes(), n)))
+    t.start()
+    t.join()
+    m.check(lib2.b200_set_device(0))
+    assert res["multi"] == c.MsmBatch(pts, ks.tobytes(), n)

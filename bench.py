@@ -290,7 +290,7 @@ def main():
         # (ncu capture profiles/r1_bench_launches.md); the algorithmic HBM bytes are 1,152 B per check
         "traffic": {"dram_bytes_per_launch": 28.6e6, "algorithmic_bytes_per_launch": 1152 * n,
                     "source": "profiles/r1_bench_launches.md"},
-        "kernel": "pairing_kernel<BLS381,2> (Miller loop x2 + final exponentiation fused)",
+        "kernel": "vm_pairing_kernel<BLS381,2> (warp-cooperative VM: Miller loop x2 + final exponentiation fused)",
         "note": "integer-multiply roofline (SURVEY 8d): algorithmic MAC32 = checks/s x %d m x 300; peak = measured "
                 "IMAD.WIDE.U32 issue rate (tools/imad_peak.cu, profiles/peaks_r1.json). HBM traffic is "
                 "1,152 B per check (<0.01%% of HBM bandwidth), so no HBM roofline applies." % M_PER_OP["bls381_pairing2_fexp"],

@@ -9,12 +9,32 @@ SRC = os.path.join(HERE, "cpu", "oracle_cpu.cpp")
 _lib = None
 
 
+def _host_signature():
+    """the .so is built with -march=native: rebuild it when the host CPU differs from the build host
+    (the build container and the GPU box are different machines)."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        sig_file = SO + ".host"
+        sig = _host_signature()
+        stale = (not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC) or not os.path.exists(sig_file)
+                 or open(sig_file).read().strip() != sig)
+        if stale:
             subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-shared", "-fPIC", "-pthread",
                                    "-o", SO, SRC])
+            with open(sig_file, "w") as f:
+                f.write(sig)
         _lib = ctypes.CDLL(SO)
         _lib.orc_hardware_threads.restype = ctypes.c_int
     return _lib

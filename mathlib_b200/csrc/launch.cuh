@@ -97,6 +97,20 @@ struct Launch {
         }
         return vm_pairing(np, n, g1a, g2a, g1b, g2b, out, flags, err, s);
     }
+    // batches that cannot fill every SM with full-size blocks use the 4-warp variant (20 products per block)
+    static bool small_batch(size_t n) { return n < (size_t)148 * vm_warps<C>() * B200_VM_GROUPS_PER_WARP; }
+    template <int W>
+    static void vm_launch(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                          uint8_t* out, uint32_t flags, int* err, const uint32_t* d_words, const VmDirEntry* d_dir,
+                          cudaStream_t s) {
+        const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+        const unsigned nb = (unsigned)((n + gpb - 1) / gpb);
+        const size_t smem = vm_smem_bytes<C, W>();
+        if (np == 1)
+            vm_pairing_kernel<C, 1, W><<<nb, W * 32, smem, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err, d_words, d_dir);
+        else
+            vm_pairing_kernel<C, 2, W><<<nb, W * 32, smem, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir);
+    }
     // per device: upload the microcode once and opt in to the large dynamic shared-memory carve-out
     static cudaError_t vm_setup(const uint32_t** words, const VmDirEntry** dir) {
         static thread_local int cfg_dev = -1;
@@ -105,7 +119,6 @@ struct Launch {
         cudaError_t e;
         int dev = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        const size_t smem = vm_smem_bytes<C>();
         if (cfg_dev != dev) {
             static std::mutex mu;
             static std::map<int, std::pair<const uint32_t*, const VmDirEntry*>> tables;
@@ -120,12 +133,15 @@ struct Launch {
                                     cudaMemcpyHostToDevice)) != cudaSuccess) return e;
                 if ((e = cudaMemcpy(d, VmTables<C>::host_dir(), sizeof(VmDirEntry) * VP_COUNT, cudaMemcpyHostToDevice)) !=
                     cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem)) != cudaSuccess) return e;
+                constexpr int WB = vm_warps<C>(), WS = B200_VM_WARPS_SMALL;
+                const int sb = (int)vm_smem_bytes<C, WB>(), ss = (int)vm_smem_bytes<C, WS>();
+                const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
                 it = tables.emplace(dev, std::make_pair((const uint32_t*)w, (const VmDirEntry*)d)).first;
             }
             d_words = it->second.first;
@@ -143,13 +159,8 @@ struct Launch {
         const VmDirEntry* d_dir = nullptr;
         cudaError_t e = vm_setup(&d_words, &d_dir);
         if (e != cudaSuccess) return e;
-        const size_t smem = vm_smem_bytes<C>();
-        const unsigned gpb = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
-        const unsigned nb = (unsigned)((n + gpb - 1) / gpb);
-        if (np == 1)
-            vm_pairing_kernel<C, 1><<<nb, B200_VM_WARPS * 32, smem, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err, d_words, d_dir);
-        else
-            vm_pairing_kernel<C, 2><<<nb, B200_VM_WARPS * 32, smem, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir);
+        if (small_batch(n)) vm_launch<B200_VM_WARPS_SMALL>(np, n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir, s);
+        else vm_launch<vm_warps<C>()>(np, n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir, s);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
@@ -165,9 +176,17 @@ struct Launch {
         const VmDirEntry* d_dir = nullptr;
         cudaError_t e = vm_setup(&d_words, &d_dir);
         if (e != cudaSuccess) return e;
-        const unsigned gpb = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
-        vm_fexp_kernel<C><<<(unsigned)((n + gpb - 1) / gpb), B200_VM_WARPS * 32, vm_smem_bytes<C>(), s>>>(
-            n, in, out, flags, err, d_words, d_dir);
+        if (small_batch(n)) {
+            constexpr int W = B200_VM_WARPS_SMALL;
+            const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+            vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n, in, out, flags, err,
+                                                                                                    d_words, d_dir);
+        } else {
+            constexpr int W = vm_warps<C>();
+            const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+            vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n, in, out, flags, err,
+                                                                                                    d_words, d_dir);
+        }
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }

@@ -18,6 +18,9 @@ template <class C> struct VmTables;
         static constexpr int NSLOTS = VM_##NAME##_NSLOTS;                                                 \
         static constexpr int NREGS = VM_##NAME##_NREGS;                                                   \
         static constexpr int NWORDS = VM_##NAME##_NWORDS;                                                 \
+        static constexpr int QSTRIDE = VM_##NAME##_QSTRIDE;                                               \
+        static constexpr int QBASE = VM_##NAME##_QBASE;                                                   \
+        static constexpr int PBASE = VM_##NAME##_PBASE;                                                   \
         static const uint32_t* host_words() { return H_VMW_##NAME; }                                      \
         static const VmDirEntry* host_dir() { return H_VMD_##NAME; }                                      \
     };
@@ -218,7 +221,7 @@ struct VmDriver {
                 else if (fl != 0) { *err = 1; F::zero(v); }
                 else CD::fp_from_bytes(v, g1 + r * FB, r == 0 ? (uint8_t)~CD::flag_mask() : 0xFF, err);
             }
-            uint32_t* dst = ctx.slots + (24 + k) * SW + r * N;
+            uint32_t* dst = ctx.slots + (TB::PBASE + k) * SW + r * N;
             for (int i = 0; i < N; i++) dst[i] = v.l[i];
         } else {
             int q = r - 2;                    // 0: x.c0, 1: x.c1, 2: y.c0, 3: y.c1
@@ -231,7 +234,7 @@ struct VmDriver {
                 else if (fl != 0) { *err = 1; F::zero(v); }
                 else CD::fp_from_bytes(v, g2 + pos * FB, pos == 0 ? (uint8_t)~CD::flag_mask() : 0xFF, err);
             }
-            uint32_t* dst = ctx.slots + (18 + 3 * k + (q >> 1)) * SW + (q & 1) * N;
+            uint32_t* dst = ctx.slots + (TB::QBASE + TB::QSTRIDE * k + (q >> 1)) * SW + (q & 1) * N;
             for (int i = 0; i < N; i++) dst[i] = v.l[i];
         }
         return F::is_zero(v) ? 1 : 0;
@@ -270,25 +273,32 @@ struct VmDriver {
 };
 
 #if defined(__CUDACC__)
-#define B200_VM_WARPS 4
+// resident warps per block (one block per SM): 12 = three per sub-partition, the most the register file (<= 168
+// registers per thread) and the shared memory (60 groups x 3.4 KB + microcode) allow.  The multiply sections of one warp
+// keep the FMA-heavy pipe only ~1/3 busy (dependent carry chains), so occupancy is what fills it.
+#define B200_VM_WARPS_MAX 12
+// BN254's microcode is larger (BN tail programs, 8-register final exponentiation): 10 warps keep it inside 227 KB
+template <class C> __host__ __device__ constexpr int vm_warps() { return C::N == 8 ? 10 : B200_VM_WARPS_MAX; }
 #define B200_VM_GROUPS_PER_WARP 5
 #define B200_VM_GROUP_PAD 4          // words; staggers the groups across shared-memory banks
 
 template <class C>
 __host__ __device__ constexpr size_t vm_group_stride() { return (size_t)VmTables<C>::NSLOTS * 2 * C::N + B200_VM_GROUP_PAD; }
-template <class C>
+// small batches use 4-warp blocks (20 groups) so that they spread over more SMs
+#define B200_VM_WARPS_SMALL 4
+template <class C, int WARPS>
 __host__ __device__ constexpr size_t vm_smem_bytes() {
-    return 4 * ((size_t)B200_VM_WARPS * B200_VM_GROUPS_PER_WARP * vm_group_stride<C>() + (size_t)VM_KBANK * 2 * C::N +
+    return 4 * ((size_t)WARPS * B200_VM_GROUPS_PER_WARP * vm_group_stride<C>() + (size_t)VM_KBANK * 2 * C::N +
                 (size_t)VmTables<C>::NWORDS + VP_COUNT * 2);
 }
 
-template <class C, int NP>
-__global__ void __launch_bounds__(B200_VM_WARPS * 32, 2)
+template <class C, int NP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)
 vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
                   uint8_t* out, uint32_t flags, int* err, const uint32_t* mc_words, const VmDirEntry* mc_dir) {
     extern __shared__ uint32_t smem[];
     constexpr int N = C::N;
-    constexpr int GPB = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
+    constexpr int GPB = WARPS * B200_VM_GROUPS_PER_WARP;
     uint32_t* s_slots = smem;
     uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
     uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
@@ -342,13 +352,13 @@ vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_
     }
 }
 // standalone driver.Curve.FExp on the VM (same slot file / microcode as the pairing kernel)
-template <class C>
-__global__ void __launch_bounds__(B200_VM_WARPS * 32, 2)
+template <class C, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)
 vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, const uint32_t* mc_words,
                const VmDirEntry* mc_dir) {
     extern __shared__ uint32_t smem[];
     constexpr int N = C::N;
-    constexpr int GPB = B200_VM_WARPS * B200_VM_GROUPS_PER_WARP;
+    constexpr int GPB = WARPS * B200_VM_GROUPS_PER_WARP;
     uint32_t* s_slots = smem;
     uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
     uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;

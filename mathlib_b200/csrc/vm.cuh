@@ -82,19 +82,33 @@ struct Vm {
     template <bool TWO>
     static B200_HD void wide_mac2(uint32_t* X, uint32_t* Y, const uint32_t* a0, const uint32_t* b0, const uint32_t* a1,
                                   const uint32_t* b1) {
+        // Each column sum is split into two partial sums (even / odd multiplicand index): two dependent IMAD.WIDE
+        // chains per accumulator instead of one, and a register footprint of 168 (12 resident warps per SM).
         uint32_t x0 = X[0], x1 = X[1], x2 = 0;
         uint32_t y0 = 0, y1 = 0, y2 = 0;
         if (TWO) { y0 = Y[0]; y1 = Y[1]; }
 #pragma unroll
         for (int k = 0; k < 2 * N - 1; k++) {
+            uint32_t u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;      // second partial sums of this column
+            const int ilo = (k < N ? 0 : k - N + 1), ihi = (k < N ? k : N - 1);
 #pragma unroll
-            for (int i = (k < N ? 0 : k - N + 1); i <= (k < N ? k : N - 1); i++) {
+            for (int i = ilo + (ilo & 1); i <= ihi; i += 2) {          // even multiplicand indices
                 const int j = k - i;
                 x0 = mad_lo_cc(a0[i], b0[j], x0); x1 = madc_hi_cc(a0[i], b0[j], x1); x2 = addc(x2, 0);
                 if (TWO) { y0 = mad_lo_cc(a1[i], b1[j], y0); y1 = madc_hi_cc(a1[i], b1[j], y1); y2 = addc(y2, 0); }
             }
+#pragma unroll
+            for (int i = ilo + 1 - (ilo & 1); i <= ihi; i += 2) {      // odd multiplicand indices
+                const int j = k - i;
+                u0 = mad_lo_cc(a0[i], b0[j], u0); u1 = madc_hi_cc(a0[i], b0[j], u1); u2 = addc(u2, 0);
+                if (TWO) { v0 = mad_lo_cc(a1[i], b1[j], v0); v1 = madc_hi_cc(a1[i], b1[j], v1); v2 = addc(v2, 0); }
+            }
+            x0 = add_cc(x0, u0); x1 = addc_cc(x1, u1); x2 = addc(x2, u2);
             X[k] = x0; x0 = x1; x1 = add_cc(x2, X[k + 2]); x2 = addc(0, 0);
-            if (TWO) { Y[k] = y0; y0 = y1; y1 = add_cc(y2, Y[k + 2]); y2 = addc(0, 0); }
+            if (TWO) {
+                y0 = add_cc(y0, v0); y1 = addc_cc(y1, v1); y2 = addc(y2, v2);
+                Y[k] = y0; y0 = y1; y1 = add_cc(y2, Y[k + 2]); y2 = addc(0, 0);
+            }
         }
         X[2 * N - 1] = x0; X[2 * N] = x1;
         if (TWO) { Y[2 * N - 1] = y0; Y[2 * N] = y1; }

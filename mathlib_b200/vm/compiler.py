@@ -51,6 +51,7 @@ class Val:
         self.alt = kw.get('alt')
         self.name = kw.get('name', '')
         self.out = None                   # (class, index) if bound to an output location
+        self.group = kw.get('group', 0)   # scheduling group: lower groups are scheduled first (bounds live temporaries)
         Val._n += 1
         self.id = Val._n
 
@@ -160,6 +161,8 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
     while remaining:
         ready = [v for v in remaining if all(o.id in done for o in v.operands())]
         assert ready, "cycle in program " + name
+        gmin = min(v.group for v in ready)
+        ready = [v for v in ready if v.group == gmin]
         r_lin = [v for v in ready if v.kind == 'lin']
         r_dot = [v for v in ready if v.kind == 'dot']
         r_inv = [v for v in ready if v.kind == 'inv']

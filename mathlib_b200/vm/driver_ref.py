@@ -17,6 +17,8 @@ class CurveCtx:
         self.cv = PR.CURVES[name]
         self.progs = PR.build_all(name)
         self.nslots, self.nregs = PR.SLOTCFG[name]
+        self.qstride = 3 if self.cv.family == 'bn' else 2
+        self.pbase = PR.Q_BASE + 2 * self.qstride
         # constant bank: one, b', zero, then frobenius gamma_{k,i}
         self.consts = [(1, 0), btw, (0, 0)] + [frob[k][i] for k in (1, 2, 3) for i in range(1, 6)]
 
@@ -39,9 +41,9 @@ def miller(ctx, pairs):
         live[k] = P is not None and Q is not None
         P = P or (0, 0)
         Q = Q or ((0, 0), (0, 0))
-        slots[PR.Q_BASE + 3 * k] = Q[0]
-        slots[PR.Q_BASE + 3 * k + 1] = Q[1]
-        slots[PR.P_BASE + k] = (P[0], P[1])
+        slots[PR.Q_BASE + ctx.qstride * k] = Q[0]
+        slots[PR.Q_BASE + ctx.qstride * k + 1] = Q[1]
+        slots[ctx.pbase + k] = (P[0], P[1])
     cur, nxt = 0, 6
     ctx.run('INIT%d' % np_, slots, (cur, nxt, 0), live)
     digits = loop_digits(ctx)

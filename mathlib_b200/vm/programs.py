@@ -14,16 +14,28 @@ squaring); tests/test_vm_programs.py checks every compiled program against the o
 from .compiler import (ref, const, dot, lin, inv, mul, sqr, compile_program, NEG, CONJ, XI, DBL, REAL0, REAL1,
                        C_ABS, C_B1, C_B2, C_B3, C_CONST)
 
-T_BASE, Q_BASE, P_BASE = 12, 18, 24
-MILLER_TEMP0 = 26
+T_BASE, Q_BASE = 12, 18
 # per-curve slot file: BLS12 curves (96-byte slots): 48 slots, 5 Fp12 registers for the final exponentiation;
 # BN254 (64-byte slots): 72 slots, 8 registers (the Fuentes-Castaneda chain keeps more values alive).  Both are 4,608 B.
-SLOTCFG = {'BLS381': (48, 5), 'BLS377': (48, 5), 'BN254': (72, 8)}
-_cfg = {'nslots': 48, 'nregs': 5}
+SLOTCFG = {'BLS381': (36, 5), 'BLS377': (36, 5), 'BN254': (54, 8)}
+_cfg = {'nslots': 36, 'nregs': 5, 'qstride': 2}
+
+
+def q_stride():
+    """slots per Q: (x, y) -- plus -y for BN254, whose signed NAF digits subtract Q"""
+    return _cfg['qstride']
+
+
+def p_base():
+    return Q_BASE + 2 * q_stride()
+
+
+def miller_temp0():
+    return p_base() + 2
 
 
 def miller_temps():
-    return list(range(MILLER_TEMP0, _cfg['nslots']))
+    return list(range(miller_temp0(), _cfg['nslots']))
 
 
 def fexp_temps():
@@ -116,7 +128,7 @@ def f12_inv_nodes(g):
     t0 = dot([(d0, d0), ((d1, XI | NEG), d2)])
     t1 = dot([((d2, XI), d2), ((d0, NEG), d1)])
     t2 = dot([(d1, d1), ((d0, NEG), d2)])
-    n = dot([(d0, t0), ((d2, XI), t1), ((d1, XI), t2)])
+    n = dot([(d0, t0), ((d2, XI), t1), ((d1, XI), t2)], name='norm')
     ni = inv(n)
     e = [mul(t0, ni), mul(t1, ni), mul(t2, ni)]
 
@@ -128,7 +140,23 @@ def f12_inv_nodes(g):
         return [z0, z1, z2]
     c0 = f6mul(x, e, False)
     c1 = f6mul(y, e, True)
-    return [c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]]
+    return [c0[0], c1[0], c0[1], c1[1], c0[2], c1[2]], n, ni
+
+
+def set_group(nodes, g):
+    """assign scheduling group g to every not-yet-grouped non-reference node reachable from `nodes`"""
+    seen = set()
+
+    def visit(v):
+        if v.id in seen or v.kind == 'ref':
+            return
+        seen.add(v.id)
+        if v.group == 0:
+            v.group = g
+        for o in v.operands():
+            visit(o)
+    for n in nodes:
+        visit(n)
 
 
 def regs(cls, base=0):
@@ -163,7 +191,11 @@ def prog_frob(k):
 
 
 def prog_inv():
-    return compile_program('F12_INV', bind(f12_inv_nodes(regs(C_B2)), C_B1), fexp_temps())
+    nodes, n, ni = f12_inv_nodes(regs(C_B2))
+    # the norm and its inverse are parked in two slots of the destination register (written for real only in the last
+    # phase), which keeps the program within 6 temporaries
+    outs = [(n, (C_B1, 4)), (ni, (C_B1, 5))] + bind(nodes, C_B1)
+    return compile_program('F12_INV', outs, fexp_temps())
 
 
 # ------------------------------------------------------------------------------------------------ Miller-loop programs
@@ -181,7 +213,7 @@ def _line_and_sparse(cv, f_cur, lines_per_pair, f_slots_cycle):
 
 def _double_pair(cv, k):
     X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
-    P = ref(C_ABS, P_BASE + k)
+    P = ref(C_ABS, p_base() + k)
     XY = mul(X, Y, name='XY')
     B = sqr(Y, name='B')
     C = sqr(Z, name='C')
@@ -209,7 +241,7 @@ def _double_pair(cv, k):
 
 def _add_pair(cv, k, qx, qy, update=True):
     X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
-    P = ref(C_ABS, P_BASE + k)
+    P = ref(C_ABS, p_base() + k)
     O = dot([((qy, NEG), Z)], lin=[(Y, 1)], name='O')
     L = dot([((qx, NEG), Z)], lin=[(X, 1)], name='L')
     J = dot([(qx, O), ((L, NEG), qy)], name='J')
@@ -241,29 +273,34 @@ def _f_cycle(n):
 def prog_dbl(cv, np_):
     f = regs(C_B1)
     f2 = f12_sqr_nodes(f)
+    set_group(f2, 1)
     cyc = _f_cycle(1 + np_)
     outs = bind(f2, cyc[0])
-    lines = []
+    f_cur = f2
     for k in range(np_):
         t, line = _double_pair(cv, k)
+        nodes = sparse_mul_nodes(f_cur, line, cv.supp, pred=k + 1, alt=f_cur)
+        set_group([v for v, _ in t] + nodes, 2 + k)       # one pair at a time: bounds the live temporaries
         outs += t
-        lines.append(line)
-    so, _ = _line_and_sparse(cv, f2, lines, cyc[1:])
-    outs += so
+        outs += bind(nodes, cyc[1 + k])
+        f_cur = nodes
     return compile_program('DBL%d' % np_, outs, miller_temps())
 
 
 def prog_add(cv, np_):
     f = regs(C_B1)
-    outs, lines = [], []
+    outs = []
+    cyc = _f_cycle(np_)
+    f_cur = f
     for k in range(np_):
-        qx = ref(C_ABS, Q_BASE + 3 * k)
-        qy = ref(C_B3, Q_BASE + 3 * k + 1)
+        qx = ref(C_ABS, Q_BASE + q_stride() * k)
+        qy = ref(C_B3, Q_BASE + q_stride() * k + 1)
         t, line = _add_pair(cv, k, qx, qy)
+        nodes = sparse_mul_nodes(f_cur, line, cv.supp, pred=k + 1, alt=f_cur)
+        set_group([v for v, _ in t] + nodes, 1 + k)
         outs += t
-        lines.append(line)
-    so, _ = _line_and_sparse(cv, f, lines, _f_cycle(np_))
-    outs += so
+        outs += bind(nodes, cyc[k])
+        f_cur = nodes
     return compile_program('ADD%d' % np_, outs, miller_temps())
 
 
@@ -275,12 +312,12 @@ def prog_bn_tail(cv, np_):
     cyc = _f_cycle(2 * np_)
     ci = 0
     for k in range(np_):
-        qx, qy = ref(C_ABS, Q_BASE + 3 * k), ref(C_ABS, Q_BASE + 3 * k + 1)
+        qx, qy = ref(C_ABS, Q_BASE + q_stride() * k), ref(C_ABS, Q_BASE + q_stride() * k + 1)
         q1x = dot([((qx, CONJ), const(k_frob(1, 2)))])
         q1y = dot([((qy, CONJ), const(k_frob(1, 3)))])
         q2x = dot([(qx, const(k_frob(2, 2)))])
         X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
-        P = ref(C_ABS, P_BASE + k)
+        P = ref(C_ABS, p_base() + k)
         # first step (with update), written out here because the second step needs the NEW T as DAG nodes
         O = dot([((q1y, NEG), Z)], lin=[(Y, 1)])
         L = dot([((q1x, NEG), Z)], lin=[(X, 1)])
@@ -298,6 +335,7 @@ def prog_bn_tail(cv, np_):
         line2 = {0: dot([(L2, (P, REAL1))]), 1: dot([((O2, NEG), (P, REAL0))]), 3: J2}
         for line in (line1, line2):
             nodes = sparse_mul_nodes(f_cur, line, cv.supp, pred=k + 1, alt=f_cur)
+            set_group(nodes, 1 + k)
             outs += bind(nodes, cyc[ci])
             ci += 1
             f_cur = nodes
@@ -310,9 +348,10 @@ def prog_init(np_):
     outs = [(lin([(one if k == 0 else zero, 1)]), (C_B1, k)) for k in range(6)]
     for k in range(np_):
         outs.append((lin([(one, 1)]), (C_ABS, T_BASE + 3 * k + 2)))
-        outs.append((lin([(ref(C_ABS, Q_BASE + 3 * k), 1)]), (C_ABS, T_BASE + 3 * k)))
-        outs.append((lin([(ref(C_ABS, Q_BASE + 3 * k + 1), 1)]), (C_ABS, T_BASE + 3 * k + 1)))
-        outs.append((lin([((ref(C_ABS, Q_BASE + 3 * k + 1), NEG), 1)]), (C_ABS, Q_BASE + 3 * k + 2)))
+        outs.append((lin([(ref(C_ABS, Q_BASE + q_stride() * k), 1)]), (C_ABS, T_BASE + 3 * k)))
+        outs.append((lin([(ref(C_ABS, Q_BASE + q_stride() * k + 1), 1)]), (C_ABS, T_BASE + 3 * k + 1)))
+        if q_stride() == 3:
+            outs.append((lin([((ref(C_ABS, Q_BASE + q_stride() * k + 1), NEG), 1)]), (C_ABS, Q_BASE + q_stride() * k + 2)))
     return compile_program('INIT%d' % np_, outs, miller_temps())
 
 
@@ -320,6 +359,7 @@ def build_all(curve_name):
     """name -> Program for one curve"""
     cv = CURVES[curve_name]
     _cfg['nslots'], _cfg['nregs'] = SLOTCFG[curve_name]
+    _cfg['qstride'] = 3 if cv.family == 'bn' else 2
     progs = {}
     for np_ in (1, 2):
         progs['INIT%d' % np_] = prog_init(np_)

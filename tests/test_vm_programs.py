@@ -44,5 +44,5 @@ def test_program_budgets():
         nslots, nregs = PR.SLOTCFG[name]
         for pn, p in progs.items():
             assert len(p.words) % (12 * 6) == 0
-        assert progs['DBL2'].temps_used <= nslots - PR.MILLER_TEMP0
+        assert progs['DBL2'].temps_used <= nslots - PR.miller_temp0()
         assert progs['F12_INV'].temps_used <= nslots - 6 * nregs

@@ -273,10 +273,10 @@ struct VmDriver {
 };
 
 #if defined(__CUDACC__)
-// resident warps per block (one block per SM): 12 = three per sub-partition, the most the register file (<= 168
-// registers per thread) and the shared memory (60 groups x 3.4 KB + microcode) allow.  The multiply sections of one warp
-// keep the FMA-heavy pipe only ~1/3 busy (dependent carry chains), so occupancy is what fills it.
-#define B200_VM_WARPS_MAX 12
+// Block shape.  BLS12 curves: 4 warps (20 groups) per block, two blocks per SM -- the operand-scanning wide product needs
+// ~200 registers, so 8 resident warps is the register-file limit (12 warps need <= 168 registers, which the slower
+// product-scanning variant reaches: measured 103.7 ms vs 99.9 ms per 65,536 checks for this shape).
+#define B200_VM_WARPS_MAX 4
 // BN254's microcode is larger (BN tail programs, 8-register final exponentiation): 10 warps keep it inside 227 KB
 template <class C> __host__ __device__ constexpr int vm_warps() { return C::N == 8 ? 10 : B200_VM_WARPS_MAX; }
 #define B200_VM_GROUPS_PER_WARP 5

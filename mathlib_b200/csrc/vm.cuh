@@ -74,44 +74,56 @@ struct Vm {
     // wide arithmetic
     // ---------------------------------------------------------------------------------------------------
     static constexpr int AW = 2 * N + 2;         // words of an even / odd accumulator array
-    // Product-scanning multiply-accumulate of one or two independent wide accumulators in lock-step:
-    //   X += a0*b0  [and  Y += a1*b1]          (unreduced, W words each)
-    // Column k collects the products a[i]*b[k-i] in a 96-bit running sum (c0,c1,c2): one IMAD.WIDE.U32 (carry out)
-    // plus one IADD3.X per product.  Each accumulator is one dependent chain.  The Karatsuba cross term is accumulated
-    // in a second call so that the register footprint stays below 168 (12 resident warps per SM).
-    template <bool TWO>
-    static B200_HD void wide_mac2(uint32_t* X, uint32_t* Y, const uint32_t* a0, const uint32_t* b0, const uint32_t* a1,
-                                  const uint32_t* b1) {
-        // Each column sum is split into two partial sums (even / odd multiplicand index): two dependent IMAD.WIDE
-        // chains per accumulator instead of one, and a register footprint of 168 (12 resident warps per SM).
-        uint32_t x0 = X[0], x1 = X[1], x2 = 0;
-        uint32_t y0 = 0, y1 = 0, y2 = 0;
-        if (TWO) { y0 = Y[0]; y1 = Y[1]; }
+    // v[0..2N) = a * b, unreduced.  Operand scanning with the products split by the parity of their word position:
+    // a[j]*b[i] lands on word i+j; even positions accumulate in Ev, odd ones in Od (Od[k] holds word k+1).  Every
+    // 32x32 product is one IMAD.WIDE.U32.X inside a carry chain (two independent chains per row) -- one instruction
+    // per multiply-accumulate, against two for a product-scanning column sum.  The two halves are merged at the end.
+    static B200_HD void wide_mul(uint32_t* v, const uint32_t* a, const uint32_t* b) {
+        uint32_t Ev[2 * N + 1], Od[2 * N];
+        // row 0: plain products
 #pragma unroll
-        for (int k = 0; k < 2 * N - 1; k++) {
-            uint32_t u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;      // second partial sums of this column
-            const int ilo = (k < N ? 0 : k - N + 1), ihi = (k < N ? k : N - 1);
+        for (int j = 0; j < N; j += 2) {
+            Ev[j] = mul_lo(a[j], b[0]);
+            Ev[j + 1] = mul_hi(a[j], b[0]);
+            Od[j] = mul_lo(a[j + 1], b[0]);
+            Od[j + 1] = mul_hi(a[j + 1], b[0]);
+        }
 #pragma unroll
-            for (int i = ilo + (ilo & 1); i <= ihi; i += 2) {          // even multiplicand indices
-                const int j = k - i;
-                x0 = mad_lo_cc(a0[i], b0[j], x0); x1 = madc_hi_cc(a0[i], b0[j], x1); x2 = addc(x2, 0);
-                if (TWO) { y0 = mad_lo_cc(a1[i], b1[j], y0); y1 = madc_hi_cc(a1[i], b1[j], y1); y2 = addc(y2, 0); }
+        for (int k = N; k < 2 * N + 1; k++) Ev[k] = 0;
+#pragma unroll
+        for (int k = N; k < 2 * N; k++) Od[k] = 0;
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const int je = i & 1;          // first j with (i+j) even
+            const int jo = je ^ 1;         // first j with (i+j) odd
+            {
+                const int w0 = i + je;
+                Ev[w0] = mad_lo_cc(a[je], b[i], Ev[w0]);
+                Ev[w0 + 1] = madc_hi_cc(a[je], b[i], Ev[w0 + 1]);
+#pragma unroll
+                for (int j = je + 2; j < N; j += 2) {
+                    Ev[i + j] = madc_lo_cc(a[j], b[i], Ev[i + j]);
+                    Ev[i + j + 1] = madc_hi_cc(a[j], b[i], Ev[i + j + 1]);
+                }
+                Ev[w0 + N] = addc(Ev[w0 + N], 0);      // so far only carries live up there: cannot overflow
             }
+            {
+                const int w0 = i + jo - 1;
+                Od[w0] = mad_lo_cc(a[jo], b[i], Od[w0]);
+                Od[w0 + 1] = madc_hi_cc(a[jo], b[i], Od[w0 + 1]);
 #pragma unroll
-            for (int i = ilo + 1 - (ilo & 1); i <= ihi; i += 2) {      // odd multiplicand indices
-                const int j = k - i;
-                u0 = mad_lo_cc(a0[i], b0[j], u0); u1 = madc_hi_cc(a0[i], b0[j], u1); u2 = addc(u2, 0);
-                if (TWO) { v0 = mad_lo_cc(a1[i], b1[j], v0); v1 = madc_hi_cc(a1[i], b1[j], v1); v2 = addc(v2, 0); }
-            }
-            x0 = add_cc(x0, u0); x1 = addc_cc(x1, u1); x2 = addc(x2, u2);
-            X[k] = x0; x0 = x1; x1 = add_cc(x2, X[k + 2]); x2 = addc(0, 0);
-            if (TWO) {
-                y0 = add_cc(y0, v0); y1 = addc_cc(y1, v1); y2 = addc(y2, v2);
-                Y[k] = y0; y0 = y1; y1 = add_cc(y2, Y[k + 2]); y2 = addc(0, 0);
+                for (int j = jo + 2; j < N; j += 2) {
+                    Od[i + j - 1] = madc_lo_cc(a[j], b[i], Od[i + j - 1]);
+                    Od[i + j] = madc_hi_cc(a[j], b[i], Od[i + j]);
+                }
+                if (w0 + N < 2 * N) Od[w0 + N] = addc(Od[w0 + N], 0);
             }
         }
-        X[2 * N - 1] = x0; X[2 * N] = x1;
-        if (TWO) { Y[2 * N - 1] = y0; Y[2 * N] = y1; }
+        v[0] = Ev[0];
+        v[1] = add_cc(Ev[1], Od[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
+        v[2 * N - 1] = addc(Ev[2 * N - 1], Od[2 * N - 2]);
     }
     // v[0..W) = Ev + (Od << 32)
     static B200_HD void wide_merge(uint32_t* v, const uint32_t* Ev, const uint32_t* Od) {
@@ -121,17 +133,18 @@ struct Vm {
         for (int k = 2; k < W - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
         v[W - 1] = addc(Ev[W - 1], Od[W - 2]);
     }
+    // acc (W words, two's complement while partial sums are pending) +/-= v (2N words)
     static B200_HD void wide_add(uint32_t* acc, const uint32_t* v) {
         acc[0] = add_cc(acc[0], v[0]);
 #pragma unroll
-        for (int k = 1; k < W - 1; k++) acc[k] = addc_cc(acc[k], v[k]);
-        acc[W - 1] = addc(acc[W - 1], v[W - 1]);
+        for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], v[k]);
+        acc[2 * N] = addc(acc[2 * N], 0);
     }
     static B200_HD void wide_sub(uint32_t* acc, const uint32_t* v) {
         acc[0] = sub_cc(acc[0], v[0]);
 #pragma unroll
-        for (int k = 1; k < W - 1; k++) acc[k] = subc_cc(acc[k], v[k]);
-        acc[W - 1] = subc(acc[W - 1], v[W - 1]);
+        for (int k = 1; k < 2 * N; k++) acc[k] = subc_cc(acc[k], v[k]);
+        acc[2 * N] = subc(acc[2 * N], 0);
     }
     // Montgomery reduction of a wide value T < 4 p R (T[0..2N), top word zero) -> canonical residue T / R mod p.
     // Word-sliding reduction on an even / odd split of T: no data movement, the window offsets are compile-time.
@@ -257,10 +270,16 @@ struct Vm {
             return;
         }
         if (kind == VM_DOT) {
-            // X = sum a0 b0, Y = sum a1 b1, Z = sum (a0+a1)(b0+b1), all unreduced
-            uint32_t Xm[W], Ym[W], IM[W];
+            // Karatsuba over Fp2 with lazy reduction: per term v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) (unreduced);
+            //   RE = nt*|BETA|*p^2 + sum (v0 + BETA v1)      IM = sum (v2 - v0 - v1)
+            // the p^2 offset keeps RE non-negative; IM may dip below zero between its updates (two's complement).
+            uint32_t RE[W], IM[W];
+            {
+                const uint32_t* off = C::K().p2 + (nt * (C::BETA == -1 ? 1 : 5)) * (2 * N);
 #pragma unroll
-            for (int k = 0; k < W; k++) { Xm[k] = 0; Ym[k] = 0; IM[k] = 0; }
+                for (int k = 0; k < 2 * N; k++) { RE[k] = off[k]; IM[k] = 0; }
+                RE[2 * N] = 0; IM[2 * N] = 0;
+            }
             for (uint32_t t = 0; t < nt; t++) {
                 const uint32_t tw = w[2 + t];
                 E2 a, b;
@@ -272,34 +291,31 @@ struct Vm {
                 const bool real_b = (bm & (VM_REAL0 | VM_REAL1)) != 0;
                 if (real_b) {
                     if (bm & VM_REAL1) b.c0 = b.c1;
-                    F::zero(b.c1);
                 } else if (bm & 3) {
                     apply_mod(b, bm & 3);
                 }
-                if (real_b) wide_mac2<false>(Xm, Ym, a.c0.l, b.c0.l, a.c1.l, b.c1.l);
-                else wide_mac2<true>(Xm, Ym, a.c0.l, b.c0.l, a.c1.l, b.c1.l);
-                // sums (a0+a1), (b0+b1) stay below 2p < 2^(32N); for a real b this is (a0+a1) * s.  Formed in place:
-                // the halves are dead after the X / Y products
-                a.c0.l[0] = add_cc(a.c0.l[0], a.c1.l[0]);
+                uint32_t v[2 * N];
+                wide_mul(v, a.c0.l, b.c0.l);               // v0
+                wide_add(RE, v);
+                if (!real_b) {
+                    wide_sub(IM, v);
+                    wide_mul(v, a.c1.l, b.c1.l);           // v1
+                    wide_sub(IM, v);
+                    wide_sub(RE, v);
+                    if (C::BETA == -5) { wide_sub(RE, v); wide_sub(RE, v); wide_sub(RE, v); wide_sub(RE, v); }
+                    // sums stay below 2p < 2^(32N); formed in place (the halves are dead now)
+                    a.c0.l[0] = add_cc(a.c0.l[0], a.c1.l[0]);
 #pragma unroll
-                for (int i = 1; i < N; i++) a.c0.l[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
-                b.c0.l[0] = add_cc(b.c0.l[0], b.c1.l[0]);
+                    for (int i = 1; i < N; i++) a.c0.l[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
+                    b.c0.l[0] = add_cc(b.c0.l[0], b.c1.l[0]);
 #pragma unroll
-                for (int i = 1; i < N; i++) b.c0.l[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
-                wide_mac2<false>(IM, IM, a.c0.l, b.c0.l, a.c0.l, b.c0.l);
-            }
-            uint32_t RE[W];
-            {
-                wide_sub(IM, Xm);
-                wide_sub(IM, Ym);                           // IM = Z - X - Y >= 0
-                // RE = X + nt*|BETA|*p^2 - |BETA|*Y  (offset keeps it non-negative, multiple of p)
-                const uint32_t* off = C::K().p2 + (nt * (C::BETA == -1 ? 1 : 5)) * (2 * N);
-#pragma unroll
-                for (int k = 0; k < 2 * N; k++) RE[k] = off[k];
-                RE[2 * N] = 0;
-                wide_add(RE, Xm);
-                wide_sub(RE, Ym);
-                if (C::BETA == -5) { wide_sub(RE, Ym); wide_sub(RE, Ym); wide_sub(RE, Ym); wide_sub(RE, Ym); }
+                    for (int i = 1; i < N; i++) b.c0.l[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
+                    wide_mul(v, a.c0.l, b.c0.l);           // v2
+                    wide_add(IM, v);
+                } else {
+                    wide_mul(v, a.c1.l, b.c0.l);           // imaginary part a1 * s
+                    wide_add(IM, v);
+                }
             }
             redc(res.c0, RE);
             redc(res.c1, IM);

@@ -288,8 +288,9 @@ def main():
         "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one vm_pairing_kernel<BLS381,2> launch at this batch size
         # (ncu capture profiles/r1_bench_launches.md); the algorithmic HBM bytes are 1,152 B per check
-        "traffic": {"dram_bytes_per_launch": 28.6e6, "algorithmic_bytes_per_launch": 1152 * n,
-                    "source": "profiles/r1_bench_launches.md"},
+        "traffic": 28.5e6 * n / 65536,
+        "traffic_detail": {"dram_bytes_per_launch_at_65536_checks": 28.5e6, "algorithmic_bytes_per_launch": 1152 * n,
+                           "source": "profiles/r1_bench_launches.md"},
         "kernel": "vm_pairing_kernel<BLS381,2> (warp-cooperative VM: Miller loop x2 + final exponentiation fused)",
         "note": "integer-multiply roofline (SURVEY 8d): algorithmic MAC32 = checks/s x %d m x 300; peak = measured "
                 "IMAD.WIDE.U32 issue rate (tools/imad_peak.cu, profiles/peaks_r1.json). HBM traffic is "
@@ -388,8 +389,44 @@ def run_extra(m, lib, dev, stream, torch):
     o = torch.empty(c.G1ByteSize, dtype=torch.uint8, device=dev)
     ms = timed(lambda: m.check(lib.b200_g1_msm(5, n, pts.data_ptr(), d_k2.data_ptr(), o.data_ptr(),
                                                m.DEVICE_PTRS | m.IN_MONT)))
-    out["config2_bls12_381_g1_msm_2^20"] = {"latency_ms": ms, "points_per_s": n / ms * 1e3,
-                                            "hbm_GBps_algorithmic": n * 128 / (ms * 1e-3) / 1e9}
+    want = o.cpu().numpy().tobytes()
+    res = {"latency_ms": ms, "points_per_s": n / ms * 1e3, "hbm_GBps_algorithmic": n * 128 / (ms * 1e-3) / 1e9,
+           "what": "points (Montgomery slab) and scalars already in HBM"}
+    # (i) bases resident with per-window tables, scalars uploaded from pinned host memory, result read back
+    import ctypes
+    h = ctypes.c_uint64()
+    t0 = time.perf_counter()
+    m.check(lib.b200_bases_upload(5, n, pts.data_ptr(), m.DEVICE_PTRS | m.IN_MONT | m.BASES_TABLES, ctypes.byref(h)))
+    torch.cuda.synchronize()
+    res["tables_upload_ms"] = (time.perf_counter() - t0) * 1e3
+    ms_t = timed(lambda: m.check(lib.b200_g1_msm_resident(h.value, n, d_k2.data_ptr(), o.data_ptr(),
+                                                          m.DEVICE_PTRS)))
+    if o.cpu().numpy().tobytes() != want:
+        raise RuntimeError("window-table MSM disagrees with the one-shot MSM")
+    res["resident_tables_latency_ms"] = ms_t
+    h_k2 = torch.from_numpy(ks2.reshape(-1)).pin_memory()
+    h_o = ctypes.create_string_buffer(c.G1ByteSize)
+
+    def wall(fn, reps=3):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best * 1e3
+    res["resident_tables_scalars_from_host_ms"] = wall(
+        lambda: m.check(lib.b200_g1_msm_resident(h.value, n, h_k2.data_ptr(), h_o, 0)))
+    if h_o.raw != want:
+        raise RuntimeError("host-scalar resident MSM disagrees")
+    m.check(lib.b200_bases_free(h.value))
+    # (ii) everything from host: 2^20 points in Bytes() form + scalars cross PCIe inside the timed region
+    m.check(lib.b200_g1_mul_batch(5, n, gen.data_ptr(), d_k.data_ptr(), pts.data_ptr(), m.DEVICE_PTRS))
+    h_pts = pts.cpu().pin_memory()
+    res["all_from_host_ms"] = wall(lambda: m.check(lib.b200_g1_msm(5, n, h_pts.data_ptr(), h_k2.data_ptr(), h_o, 0)), reps=2)
+    if h_o.raw != want:
+        raise RuntimeError("host-buffer MSM disagrees")
+    out["config2_bls12_381_g1_msm_2^20"] = res
     return out
 
 

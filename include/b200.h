@@ -54,6 +54,10 @@ extern "C" {
 #define B200_OUT_UNITY_ONLY 0x8u /* pairing / fexp: write one byte per item: 1 if the result is 1 (Gt.IsUnity), else 0 */
 #define B200_DEVICE_PTRS 0x10u   /* all buffers are device pointers on the current device (no copies, async on the
                                     stream set with b200_set_stream; caller synchronises) */
+#define B200_BASES_TABLES 0x20u  /* b200_bases_upload: also store 2^(c*w) * P_i for every Pippenger window w (W x the
+                                    memory, one-time cost of c*(W-1) doublings per point); MSMs against the handle then
+                                    skip the Horner tail.  Ignored (plain bases kept) when the table would exceed 1/4 of
+                                    the device memory. */
 
 /* error codes */
 #define B200_OK 0

@@ -16,6 +16,7 @@ IN_MONT = 0x2
 OUT_MONT = 0x4
 OUT_UNITY_ONLY = 0x8
 DEVICE_PTRS = 0x10
+BASES_TABLES = 0x20
 
 ERR_CUDA, ERR_ARG, ERR_ENCODING, ERR_NOGPU = -1, -2, -3, -4
 

@@ -191,7 +191,18 @@ uint32_t kernel_flags(uint32_t flags) { return flags & (B200_FEXP | B200_IN_MONT
 
 struct Bases {
     int curve; int dev; size_t n; void* pts;
+    int table_c; int table_w;          // window tables present when table_w > 0 (pts holds table_w * n points)
 };
+// plan of an MSM of n scalars against resident bases: the window tables are used when their window size is the one
+// this n would pick anyway (much smaller calls fall back to the plain points, which are table row 0)
+MsmPlan resident_plan(const CurveVTable* vt, const Bases* bs, size_t n) {
+    MsmPlan pl = msm_plan(n ? n : 1, vt->scalar_bits);
+    if (bs && bs->table_w > 0 && pl.c == bs->table_c && pl.W == bs->table_w) {
+        pl.tables = 1;
+        pl.stride = bs->n;
+    }
+    return pl;
+}
 std::map<uint64_t, Bases> g_bases;
 uint64_t g_next_handle = 1;
 
@@ -220,7 +231,7 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
 
 // MSM of host points/scalars [lo,hi) on one device -> one affine point written to out_host
 int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const void* pts, const void* resident_pts,
-                   const void* scalars, void* out_host, uint32_t flags) {
+                   const void* scalars, void* out_host, uint32_t flags, const Bases* bs = nullptr) {
     const CurveVTable* vt = ci.vt;
     size_t m = hi - lo;
     size_t g1sz = 2 * (size_t)vt->fp_bytes;
@@ -228,7 +239,7 @@ int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const voi
     if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
     Workspace& w = *g.w;
     CU(cudaSetDevice(dev));
-    MsmPlan pl = msm_plan(m ? m : 1, vt->scalar_bits);
+    MsmPlan pl = resident_plan(vt, bs, m);
     MsmBuffers b;
     uint8_t *d_sc = nullptr, *d_pin = nullptr, *d_out = nullptr;
     bool need_points = resident_pts == nullptr;
@@ -474,7 +485,7 @@ int b200_g1_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags)
 }
 
 static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool prepared, const void* scalars,
-                           void* out, uint32_t flags) {
+                           void* out, uint32_t flags, const Bases* bs = nullptr) {
     // device-pointer MSM: the workspace comes from the pool and is held until the stream is synchronised by the
     // caller, so it is acquired per thread and kept (thread-local) instead of being released.
     thread_local std::map<int, Workspace*> t_ws;
@@ -484,7 +495,7 @@ static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool 
     Workspace*& w = t_ws[dev];
     if (!w) w = ws_acquire(dev);
     if (!w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
-    MsmPlan pl = msm_plan(n ? n : 1, vt->scalar_bits);
+    MsmPlan pl = resident_plan(vt, bs, n);
     MsmBuffers b;
     bool need_points = !prepared;
     size_t need = msm_carve(vt, pl, n, need_points, nullptr, &b, nullptr, nullptr, 0, nullptr);
@@ -545,11 +556,20 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
     int dev = current_device();
     CU(cudaSetDevice(dev));
     void* d_pts = nullptr;
-    CU(cudaMalloc(&d_pts, (n ? n : 1) * vt->aff_size));
+    MsmPlan tp = msm_plan(n ? n : 1, vt->scalar_bits);
+    int rows = 1;
+    if ((flags & B200_BASES_TABLES) && n && tp.W > 1) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        size_t need = (size_t)tp.W * n * vt->aff_size;
+        if (need <= total_b / 4 && need <= free_b / 2) rows = tp.W;
+    }
+    CU(cudaMalloc(&d_pts, (n ? n : 1) * vt->aff_size * rows));
     size_t g1sz = 2 * (size_t)vt->fp_bytes;
     if (n) {
         if (flags & B200_DEVICE_PTRS) {
             CU(vt->msm_points(n, (const uint8_t*)pts, d_pts, kernel_flags(flags), device_err_flag(dev), t_stream));
+            if (rows > 1) CU(vt->msm_tables(n, tp.c, tp.W, n, d_pts, t_stream));
             CU(cudaStreamSynchronize(t_stream));
         } else {
             WsGuard g(dev);
@@ -559,6 +579,7 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
             CU(cudaMemcpyAsync(w.buf, pts, n * g1sz, cudaMemcpyHostToDevice, w.stream));
             CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
             CU(vt->msm_points(n, w.buf, d_pts, kernel_flags(flags), w.d_err, w.stream));
+            if (rows > 1) CU(vt->msm_tables(n, tp.c, tp.W, n, d_pts, w.stream));
             int h_err = 0;
             CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
             CU(cudaStreamSynchronize(w.stream));
@@ -567,7 +588,7 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
     }
     std::lock_guard<std::mutex> lk(g_mu);
     uint64_t h = g_next_handle++;
-    g_bases[h] = {curve, dev, n, d_pts};
+    g_bases[h] = {curve, dev, n, d_pts, rows > 1 ? tp.c : 0, rows > 1 ? tp.W : 0};
     *handle = h;
     return 0;
 }
@@ -588,11 +609,11 @@ int b200_g1_msm_resident(uint64_t handle, size_t n, const void* scalars, void* o
     if (flags & B200_DEVICE_PTRS) {
         int saved = t_device;
         t_device = bs.dev;
-        int r = msm_device_ptrs(ci, n, bs.pts, true, scalars, out, flags);
+        int r = msm_device_ptrs(ci, n, bs.pts, true, scalars, out, flags, &bs);
         t_device = saved;
         return r;
     }
-    return msm_host_range(ci, bs.dev, 0, n, nullptr, bs.pts, scalars, out, flags);
+    return msm_host_range(ci, bs.dev, 0, n, nullptr, bs.pts, scalars, out, flags, &bs);
 }
 
 int b200_bases_free(uint64_t handle) {

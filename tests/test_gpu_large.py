@@ -167,6 +167,33 @@ def test_resident_bases_and_threads(m):
         assert results[i] == (ref if i % 2 else want)
 
 
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_resident_window_tables(m, cid):
+    """B200_BASES_TABLES: resident bases carrying 2^(c*w)*P_i per window give the same MSM bytes as the one-shot path,
+    for the table's own plan (n == bases) and for a much smaller prefix (which falls back to the plain points)."""
+    import ctypes
+    lib = m.load()
+    c = m.Curves[cid]
+    n = 3000
+    g1a = rand_inputs(m, cid, n, seed=17)[0]
+    # an infinity base and a repeated base in the table
+    sz = c.G1ByteSize
+    inf = c.NewG1().Bytes()
+    g1a = inf + g1a[sz:2 * sz] + g1a[sz:2 * sz] + g1a[3 * sz:]
+    rnd = random.Random(8)
+    ks = b"".join(rnd.randrange(c.order).to_bytes(32, "big") for _ in range(n))
+    h = ctypes.c_uint64()
+    m.check(lib.b200_bases_upload(cid, n, m.buf_ptr(g1a), m.BASES_TABLES, ctypes.byref(h)))
+    out = ctypes.create_string_buffer(sz)
+    m.check(lib.b200_g1_msm_resident(h.value, n, m.buf_ptr(ks), out, 0))
+    assert out.raw == c.MsmBatch(g1a, ks, n)
+    m.check(lib.b200_g1_msm_resident(h.value, n - 1, m.buf_ptr(ks), out, 0))       # same plan, shorter run
+    assert out.raw == c.MsmBatch(g1a[:(n - 1) * sz], ks[:(n - 1) * 32], n - 1)
+    m.check(lib.b200_g1_msm_resident(h.value, 50, m.buf_ptr(ks), out, 0))          # different plan: plain points
+    assert out.raw == c.MsmBatch(g1a[:50 * sz], ks[:50 * 32], 50)
+    m.check(lib.b200_bases_free(h.value))
+
+
 def test_mont_slabs_for_pairing(m):
     """IN_MONT / OUT_MONT: the zero-conversion path for gnark-layout slabs gives the same values as BYTES."""
     import ctypes

@@ -427,6 +427,62 @@ def run_extra(m, lib, dev, stream, torch):
     if h_o.raw != want:
         raise RuntimeError("host-buffer MSM disagrees")
     out["config2_bls12_381_g1_msm_2^20"] = res
+
+    # configs[3], one GPU's share: BLS12_377_GURVY MSM over 2^21 of the 2^24 points (range split, one partial sum per GPU)
+    c = m.Curves[4]
+    n = 1 << 21
+    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks[:, 0] &= 0x0F                                           # < 2^252 < r
+    d_k = torch.from_numpy(ks.reshape(-1)).to(dev)
+    gen = torch.frombuffer(bytearray(c.GenG1.Bytes()), dtype=torch.uint8).to(dev).repeat(n)
+    pts = torch.empty(n * c.G1ByteSize, dtype=torch.uint8, device=dev)
+    m.check(lib.b200_g1_mul_batch(4, n, gen.data_ptr(), d_k.data_ptr(), pts.data_ptr(), m.DEVICE_PTRS | m.OUT_MONT))
+    ks2 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks2[:, 0] &= 0x0F
+    d_k2 = torch.from_numpy(ks2.reshape(-1)).to(dev)
+    o = torch.empty(c.G1ByteSize, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: m.check(lib.b200_g1_msm(4, n, pts.data_ptr(), d_k2.data_ptr(), o.data_ptr(),
+                                               m.DEVICE_PTRS | m.IN_MONT)), reps=2)
+    out["config3_bls12_377_g1_msm_2^21_per_gpu_share"] = {"latency_ms": ms, "points_per_s": n / ms * 1e3}
+    del gen, pts, d_k, d_k2
+
+    # configs[4], one GPU's share: 12,500 BBS-style verifications = Mul2 (B = [e]G1 + [f]A) feeding Pairing2+FExp ->
+    # IsUnity on the device, G2 arguments fixed (public key, generator); every second signature is valid
+    import random
+    c = m.Curves[6]
+    n = 12500
+    with open(os.path.join(ROOT, "tests", "golden", "g2_pool.json")) as f:
+        pk = json.load(f)["3"][0]
+    rnd = random.Random(11)
+    r, bj = c.order, int(pk["b"], 16)
+    a = [rnd.randrange(1, r) for _ in range(n)]
+    fs = [rnd.randrange(1, r) for _ in range(n)]
+    es = [(-a[i] * bj - fs[i] * a[i]) % r if i % 2 == 0 else rnd.randrange(1, r) for i in range(n)]
+
+    def dev_bytes(b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
+    gen = dev_bytes(c.GenG1.Bytes() * n)
+    d_a = dev_bytes(b"".join(x.to_bytes(32, "big") for x in a))
+    d_e = dev_bytes(b"".join(x.to_bytes(32, "big") for x in es))
+    d_f = dev_bytes(b"".join(x.to_bytes(32, "big") for x in fs))
+    d_pk = dev_bytes(bytes.fromhex(pk["g2"]) * n)
+    d_g2 = dev_bytes(c.GenG2.Bytes() * n)
+    d_A = torch.empty(n * c.G1ByteSize, dtype=torch.uint8, device=dev)
+    d_B = torch.empty(n * c.G1ByteSize, dtype=torch.uint8, device=dev)
+    d_v = torch.empty(n, dtype=torch.uint8, device=dev)
+    m.check(lib.b200_g1_mul_batch(6, n, gen.data_ptr(), d_a.data_ptr(), d_A.data_ptr(), m.DEVICE_PTRS))
+
+    def verify():
+        m.check(lib.b200_g1_mul2_batch(6, n, gen.data_ptr(), d_e.data_ptr(), d_A.data_ptr(), d_f.data_ptr(),
+                                       d_B.data_ptr(), m.DEVICE_PTRS))
+        m.check(lib.b200_pairing2_batch(6, n, d_A.data_ptr(), d_pk.data_ptr(), d_B.data_ptr(), d_g2.data_ptr(),
+                                        d_v.data_ptr(), m.DEVICE_PTRS | m.FEXP | m.OUT_UNITY_ONLY))
+    ms = timed(verify)
+    v = d_v.cpu().numpy()
+    if not (v == np.array([1 - (i & 1) for i in range(n)], dtype=np.uint8)).all():
+        raise RuntimeError("BBS-style verification verdicts are wrong")
+    out["config4_bls12_381_bbs_verify_12500_per_gpu_share"] = {"ms": ms, "verifications_per_s": n / ms * 1e3,
+                                                               "what": "Mul2 -> Pairing2+FExp -> IsUnity, device resident"}
     return out
 
 

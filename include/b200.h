@@ -111,6 +111,19 @@ int b200_bases_free(uint64_t handle);
 /* sum of n G1 points (used to combine per-GPU MSM partial sums; n is small). */
 int b200_g1_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags);
 
+/* ---- callers next to the hot path; same encodings, flags and error behaviour as above ---- */
+
+/* driver.G2.Mul(Zr) for n independent (point, scalar) pairs (reference driver/math.go:307; impls bn254.go:134-139,
+   bls12-377.go:131-136, bls12381/bls12-381.go:342-351, kilic/bls12-381.go:127-137).  Output: affine G2 elements. */
+int b200_g2_mul_batch(int curve, size_t n, const void* g2_pts, const void* scalars_be32, void* out, uint32_t flags);
+/* sum of n G2 points; n = 2 is driver.G2.Add (reference driver/math.go:310; bn254.go:141, kilic/bls12-381.go:139). */
+int b200_g2_sum(int curve, size_t n, const void* g2_pts, void* out, uint32_t flags);
+/* driver.Gt.Mul / Gt.Inverse / Gt.Exp(Zr) batches (reference driver/math.go:339-360; impls bn254.go:187-203,
+   bls12-377.go:184-200, bls12381/bls12-381.go:399-419, kilic/bls12-381.go:185-210).  Exponents are 32 bytes big-endian, used as given. */
+int b200_gt_mul_batch(int curve, size_t n, const void* gt_a, const void* gt_b, void* gt_out, uint32_t flags);
+int b200_gt_inv_batch(int curve, size_t n, const void* gt_a, void* gt_out, uint32_t flags);
+int b200_gt_exp_batch(int curve, size_t n, const void* gt_a, const void* scalars_be32, void* gt_out, uint32_t flags);
+
 /* Number of kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
 uint64_t b200_launch_count(void);
 

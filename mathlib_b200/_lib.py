@@ -40,6 +40,11 @@ PROTOTYPES = {
     "b200_g1_msm_resident": (_int, [_u64, _sz, _vp, _vp, _u32]),
     "b200_bases_free": (_int, [_u64]),
     "b200_g1_sum": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g2_mul_batch": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
+    "b200_g2_sum": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_gt_mul_batch": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
+    "b200_gt_inv_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_gt_exp_batch": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
     "b200_launch_count": (_u64, []),
 }
 

@@ -547,6 +547,96 @@ int b200_g1_msm(int curve, size_t n, const void* pts, const void* scalars, void*
     return r;
 }
 
+}  // extern "C"
+
+// element-wise batch over host or device buffers: ins[k] = (pointer, element bytes), one output element per item
+template <class KFn>
+static int elementwise_batch(int curve, size_t n, std::vector<Piece> ins, void* out, size_t out_fp_mult, uint32_t flags,
+                             size_t min_per_dev, KFn kfn) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n == 0) return 0;
+    if (!out) return fail(B200_ERR_ARG, "null buffer");
+    for (auto& p : ins)
+        if (!p.host) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    const uint32_t kf = kernel_flags(flags) & ~(B200_FEXP | B200_OUT_UNITY_ONLY);
+    for (auto& p : ins)
+        if (p.elem != 32) p.elem *= (size_t)vt->fp_bytes;          // sizes are given in Fp units except 32-byte scalars
+    const size_t osz = out_fp_mult * (size_t)vt->fp_bytes;
+    if (flags & B200_DEVICE_PTRS) {
+        int dev = current_device();
+        CU(cudaSetDevice(dev));
+        for (auto& p : ins) p.dev = (uint8_t*)const_cast<void*>(p.host);
+        CU(kfn(vt, n, ins, (uint8_t*)out, kf, device_err_flag(dev), t_stream));
+        return 0;
+    }
+    auto devs = split_devices(n, min_per_dev);
+    return run_split(devs, n, [&](int dev, size_t lo, size_t hi) {
+        return staged_call(dev, lo, hi, ins, out, osz,
+                           [&](size_t m, std::vector<Piece>& p, uint8_t* d_out, int* d_err, cudaStream_t s) {
+                               return kfn(vt, m, p, d_out, kf, d_err, s);
+                           });
+    });
+}
+
+extern "C" {
+
+int b200_g2_mul_batch(int curve, size_t n, const void* pts, const void* scalars, void* out, uint32_t flags) {
+    return elementwise_batch(curve, n, {{pts, 4, nullptr}, {scalars, 32, nullptr}}, out, 4, flags, 1024,
+                             [](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out, uint32_t kf,
+                                int* d_err, cudaStream_t s) { return vt->g2_mul(m, p[0].dev, p[1].dev, d_out, kf, d_err, s); });
+}
+
+int b200_g2_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out || (n && !pts)) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    uint32_t kf = kernel_flags(flags);
+    size_t g2sz = 4 * (size_t)vt->fp_bytes;
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    if (flags & B200_DEVICE_PTRS) {
+        CU(vt->g2_sum(n, (const uint8_t*)pts, (uint8_t*)out, kf, device_err_flag(dev), t_stream));
+        return 0;
+    }
+    WsGuard g(dev);
+    if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
+    Workspace& w = *g.w;
+    if (int rc = w.reserve(align_up(n * g2sz) + g2sz)) return rc;
+    if (n) CU(cudaMemcpyAsync(w.buf, pts, n * g2sz, cudaMemcpyHostToDevice, w.stream));
+    uint8_t* d_out = w.buf + align_up(n * g2sz);
+    CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
+    CU(vt->g2_sum(n, w.buf, d_out, kf, w.d_err, w.stream));
+    int h_err = 0;
+    CU(cudaMemcpyAsync(out, d_out, g2sz, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
+    return 0;
+}
+
+int b200_gt_mul_batch(int curve, size_t n, const void* a, const void* b, void* out, uint32_t flags) {
+    return elementwise_batch(curve, n, {{a, 12, nullptr}, {b, 12, nullptr}}, out, 12, flags, 256,
+                             [](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out, uint32_t kf,
+                                int* d_err, cudaStream_t s) { return vt->gt_op(0, m, p[0].dev, p[1].dev, d_out, kf, d_err, s); });
+}
+
+int b200_gt_inv_batch(int curve, size_t n, const void* a, void* out, uint32_t flags) {
+    return elementwise_batch(curve, n, {{a, 12, nullptr}}, out, 12, flags, 256,
+                             [](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out, uint32_t kf,
+                                int* d_err, cudaStream_t s) { return vt->gt_op(1, m, p[0].dev, nullptr, d_out, kf, d_err, s); });
+}
+
+int b200_gt_exp_batch(int curve, size_t n, const void* a, const void* scalars, void* out, uint32_t flags) {
+    return elementwise_batch(curve, n, {{a, 12, nullptr}, {scalars, 32, nullptr}}, out, 12, flags, 256,
+                             [](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out, uint32_t kf,
+                                int* d_err, cudaStream_t s) { return vt->gt_op(2, m, p[0].dev, p[1].dev, d_out, kf, d_err, s); });
+}
+
 int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint64_t* handle) {
     if (int rc = ensure_init()) return rc;
     CurveInfo ci;

@@ -9,6 +9,7 @@
 #include <mutex>
 #include "msm.cuh"
 #include "pairing_vm.cuh"
+#include "g2.cuh"
 
 namespace b200 {
 
@@ -42,6 +43,12 @@ struct CurveVTable {
     cudaError_t (*g1_mul2)(size_t n, const uint8_t* P, const uint8_t* e, const uint8_t* Q, const uint8_t* f,
                            uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
     cudaError_t (*g1_sum)(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
+    // G2.Mul / G2.Add batches, Gt.Mul / Gt.Inverse / Gt.Exp batches (op = GT_OP_*)
+    cudaError_t (*g2_mul)(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
+                          cudaStream_t s);
+    cudaError_t (*g2_sum)(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
+    cudaError_t (*gt_op)(int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t flags, int* err,
+                         cudaStream_t s);
     // points -> Montgomery affine array (for MSM / resident bases)
     cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
     // resident window tables: tab[w*stride + i] = 2^(c*w) * tab[i]
@@ -140,6 +147,8 @@ struct Launch {
                 if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
                 it = tables.emplace(dev, std::make_pair((const uint32_t*)w, (const VmDirEntry*)d)).first;
             }
             d_words = it->second.first;
@@ -185,6 +194,39 @@ struct Launch {
             vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n, in, out, flags, err,
                                                                                                     d_words, d_dir);
         }
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t gt_op(int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t flags, int* err,
+                             cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        const uint32_t* d_words = nullptr;
+        const VmDirEntry* d_dir = nullptr;
+        cudaError_t e = vm_setup(&d_words, &d_dir);
+        if (e != cudaSuccess) return e;
+        if (small_batch(n)) {
+            constexpr int W = B200_VM_WARPS_SMALL;
+            const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+            vm_gt_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(op, n, a, b, out, flags,
+                                                                                                  err, d_words, d_dir);
+        } else {
+            constexpr int W = vm_warps<C>();
+            const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+            vm_gt_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(op, n, a, b, out, flags,
+                                                                                                  err, d_words, d_dir);
+        }
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t g2_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
+                              cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        g2_mul_kernel<C><<<blocks_for(n, B200_G2_THREADS), B200_G2_THREADS, 0, s>>>(n, pts, k, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t g2_sum(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
+        g2_sum_kernel<C><<<1, 32, 0, s>>>(n, pts, out, flags, err);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
@@ -264,7 +306,7 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
-                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &msm_points, &msm_tables, &msm};
+                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &msm_points, &msm_tables, &msm};
         return &t;
     }
 };

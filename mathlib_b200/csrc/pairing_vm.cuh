@@ -208,6 +208,36 @@ struct VmDriver {
         return 6u * t0;
     }
 
+    // ---- Gt.Exp (reference driver/math.go:359; impls bn254.go:187-191, kilic/bls12-381.go:185-199): the Fp12 in
+    // register 0 raised to a 256-bit exponent (32 bytes big-endian, used as given) by a left-to-right ladder of generic
+    // squarings and multiplies predicated on the group's exponent bit -- the groups of a warp run in lock-step, each on
+    // its own exponent.  `top` = number of ladder steps (warp-uniform, >= this exponent's bit length).  Same sequence as
+    // vm/driver_ref.py:gt_exp.  Returns the slot base of the result.
+    B200_HD uint32_t gt_exp(const uint8_t* k_be32, int top) {
+        const uint32_t acc = 6, tmp = 12;
+        run(VP_GT_ONE, acc, 0, 0);
+        uint32_t kw = 0;
+        for (int i = top - 1; i >= 0; i--) {
+            if (i == top - 1 || (i & 31) == 31) {
+                const uint8_t* q = k_be32 + 28 - 4 * (i >> 5);
+                kw = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+            }
+            run(VP_F12_SQR, tmp, acc, 0);
+            ctx.live = (kw >> (i & 31)) & 1u;
+            run(VP_F12_MULP, acc, tmp, 0);
+        }
+        return acc;
+    }
+    static B200_HD int scalar_bitlen(const uint8_t* k_be32) {
+        for (int b = 0; b < 32; b++)
+            if (k_be32[b]) {
+                int l = 8;
+                while (!((k_be32[b] >> (l - 1)) & 1)) l--;
+                return (31 - b) * 8 + l;
+            }
+        return 0;
+    }
+
     // ---- I/O: lane `r` of the group converts coordinate r of pair k (P.x, P.y, Q.x.c0, Q.x.c1, Q.y.c0, Q.y.c1)
     // returns 1 if the coordinate is zero; *err set on a bad encoding
     B200_HD int load_coord(int r, int k, const uint8_t* g1, const uint8_t* g2, bool mont, int* err) {
@@ -398,6 +428,60 @@ vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* e
     } else if (active) {
         D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
     }
+}
+
+// Gt.Mul / Gt.Inverse / Gt.Exp batches on the VM (reference driver/math.go:339-360, impls
+// bn254.go:187-203, kilic/bls12-381.go:185-210).  b = second operand (MUL) or 32-byte big-endian exponents (EXP).
+enum : int { GT_OP_MUL = 0, GT_OP_INV = 1, GT_OP_EXP = 2 };
+template <class C, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)
+vm_gt_kernel(int opk, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t flags, int* err,
+             const uint32_t* mc_words, const VmDirEntry* mc_dir) {
+    extern __shared__ uint32_t smem[];
+    constexpr int N = C::N;
+    constexpr int GPB = WARPS * B200_VM_GROUPS_PER_WARP;
+    uint32_t* s_slots = smem;
+    uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
+    uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
+    if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = lane / VM_G;
+    const int role = gw < B200_VM_GROUPS_PER_WARP ? lane % VM_G : -1;
+    const int gblock = warp * B200_VM_GROUPS_PER_WARP + (gw < B200_VM_GROUPS_PER_WARP ? gw : 0);
+    const size_t item = (size_t)blockIdx.x * GPB + gblock;
+    const bool active = role >= 0 && item < n;
+    VmDriver<C> D;
+    D.ctx.slots = s_slots + (size_t)gblock * vm_group_stride<C>();
+    D.ctx.kbank = s_kbank;
+    D.ctx.live = 3;
+    D.words = s_words;
+    D.dir = s_dir;
+    D.role = active ? role : -1;
+    typedef Codec<C> CD;
+    int e = 0;
+    if (active) {
+        D.load_coeff(role, 0, a + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
+        if (opk == GT_OP_MUL) D.load_coeff(role, 6, b + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
+    }
+    if (__ballot_sync(0xffffffffu, e != 0)) {
+        if (lane == 0) atomicExch(err, 1);
+        return;
+    }
+    __syncwarp();
+    uint32_t fb = 12;
+    if (opk == GT_OP_MUL) D.run(VP_F12_MUL, 12, 0, 6);
+    else if (opk == GT_OP_INV) D.run(VP_F12_INV, 12, 0, 0);
+    else {
+        const uint8_t* k = b + (active ? item : 0) * 32;
+        const int len = active ? VmDriver<C>::scalar_bitlen(k) : 0;
+        const int top = __reduce_max_sync(0xffffffffu, len);
+        fb = D.gt_exp(k, top);
+    }
+    if (active) D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
 }
 #endif
 

@@ -153,6 +153,14 @@ class G2:
     def Equals(self, o):
         return self.raw == o.raw
 
+    def Mul(self, k):
+        """driver.G2.Mul: fresh value, receiver untouched (reference driver/math.go:307)."""
+        return G2(self.curve, self.curve.G2MulBatch(self.raw, k.Bytes(), 1))
+
+    def Add(self, o):
+        """mutates the receiver (reference driver/math.go:310)."""
+        self.raw = self.curve.G2Sum([self, o]).raw
+
 
 class Gt:
     def __init__(self, curve, raw):
@@ -167,6 +175,18 @@ class Gt:
 
     def IsUnity(self):
         return self.raw == self.curve._gt_one
+
+    def Exp(self, k):
+        """driver.Gt.Exp: fresh value (reference driver/math.go:359)."""
+        return Gt(self.curve, self.curve.GtExpBatch(self.raw, k.Bytes(), 1))
+
+    def Mul(self, o):
+        """mutates the receiver (reference driver/math.go:347)."""
+        self.raw = self.curve.GtMulBatch(self.raw, o.raw, 1)
+
+    def Inverse(self):
+        """mutates the receiver (reference driver/math.go:344)."""
+        self.raw = self.curve.GtInvBatch(self.raw, 1)
 
 
 class Curve:
@@ -292,6 +312,38 @@ class Curve:
         check(lib.b200_g1_mul2_batch(self.id, n, buf_ptr(P), buf_ptr(e), buf_ptr(Q), buf_ptr(f), out, flags))
         sz = self.G1ByteSize
         return [G1(self, out.raw[i * sz:(i + 1) * sz]) for i in range(n)]
+
+    # ---- callers next to the hot path ----
+    def G2MulBatch(self, pts, scalars, n, flags=0):
+        lib = load()
+        out = ctypes.create_string_buffer(max(n * self.G2ByteSize, 1))
+        check(lib.b200_g2_mul_batch(self.id, n, buf_ptr(pts), buf_ptr(scalars), out, flags))
+        return out.raw[:n * self.G2ByteSize]
+
+    def G2Sum(self, points):
+        lib = load()
+        out = ctypes.create_string_buffer(self.G2ByteSize)
+        pts = b"".join(p.raw for p in points)
+        check(lib.b200_g2_sum(self.id, len(points), buf_ptr(pts), out, 0))
+        return G2(self, out.raw)
+
+    def GtExpBatch(self, gt, scalars, n, flags=0):
+        lib = load()
+        out = ctypes.create_string_buffer(max(n * self.GtByteSize, 1))
+        check(lib.b200_gt_exp_batch(self.id, n, buf_ptr(gt), buf_ptr(scalars), out, flags))
+        return out.raw[:n * self.GtByteSize]
+
+    def GtMulBatch(self, a, b, n, flags=0):
+        lib = load()
+        out = ctypes.create_string_buffer(max(n * self.GtByteSize, 1))
+        check(lib.b200_gt_mul_batch(self.id, n, buf_ptr(a), buf_ptr(b), out, flags))
+        return out.raw[:n * self.GtByteSize]
+
+    def GtInvBatch(self, a, n, flags=0):
+        lib = load()
+        out = ctypes.create_string_buffer(max(n * self.GtByteSize, 1))
+        check(lib.b200_gt_inv_batch(self.id, n, buf_ptr(a), out, flags))
+        return out.raw[:n * self.GtByteSize]
 
     def MsmBatch(self, pts, scalars, n, flags=0):
         lib = load()

@@ -170,6 +170,18 @@ def final_exp(ctx, slots, f_base):
     return 6 * t0
 
 
+def gt_exp(ctx, slots, k):
+    """Gt.Exp: the Fp12 in register 0 (slots 0..5) raised to the integer k >= 0 by a left-to-right square-and-multiply
+    ladder; the multiply is predicated on the exponent bit (the kernel runs the groups of a warp in lock-step, each with
+    its own exponent).  Returns the slot base of the result."""
+    acc, tmp = 1, 2
+    ctx.run('GT_ONE', slots, (6 * acc, 0, 0))
+    for i in range(k.bit_length() - 1, -1, -1):
+        ctx.run('F12_SQR', slots, (6 * tmp, 6 * acc, 0))
+        ctx.run('F12_MULP', slots, (6 * acc, 6 * tmp, 0), (bool((k >> i) & 1), True))
+    return 6 * acc
+
+
 def f12_from_slots(slots, base):
     """w-basis g0..g5 -> ((C0.B0,C0.B1,C0.B2),(C1.B0,C1.B1,C1.B2))"""
     g = slots[base:base + 6]

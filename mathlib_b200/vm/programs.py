@@ -172,6 +172,26 @@ def prog_f12_mul():
     return compile_program('F12_MUL', bind(f12_mul_nodes(regs(C_B2), regs(C_B3)), C_B1), fexp_temps())
 
 
+def prog_f12_sqr():
+    """generic Fp12 squaring (Gt.Exp on elements that need not be cyclotomic)"""
+    return compile_program('F12_SQR', bind(f12_sqr_nodes(regs(C_B2)), C_B1), fexp_temps())
+
+
+def prog_f12_mulp():
+    """B1 = live[0] ? B2 * B3 : B2   -- the conditional multiply of a square-and-multiply ladder whose exponent bit
+    differs between the groups of a warp (the bit is handed to the interpreter as the group's `live` flag)"""
+    a, b = regs(C_B2), regs(C_B3)
+    nodes = f12_mul_nodes(a, b)
+    for k, n in enumerate(nodes):
+        n.pred, n.alt = 1, a[k]
+    return compile_program('F12_MULP', bind(nodes, C_B1), fexp_temps())
+
+
+def prog_gt_one():
+    one, zero = const(K_ONE), const(K_ZERO)
+    return compile_program('GT_ONE', [(lin([(one if k == 0 else zero, 1)]), (C_B1, k)) for k in range(6)], fexp_temps())
+
+
 def prog_cyclo():
     return compile_program('CYCLO_SQR', bind(cyclo_sqr_nodes(regs(C_B2)), C_B1), fexp_temps())
 
@@ -373,4 +393,7 @@ def build_all(curve_name):
     for k in (1, 2, 3):
         progs['FROB%d' % k] = prog_frob(k)
     progs['F12_INV'] = prog_inv()
+    progs['F12_SQR'] = prog_f12_sqr()
+    progs['F12_MULP'] = prog_f12_mulp()
+    progs['GT_ONE'] = prog_gt_one()
     return progs

@@ -99,6 +99,30 @@ def gen(curve_id, seed):
                       "scalars": "".join(h(int(k).to_bytes(32, "big")) for k in ks),
                       "out": g1b(C.g1_msm(pts_, ks))})
     out["msm"] = cases
+
+    # ---- G2.Mul / G2.Add (appended after the hot-path cases so their seeded values are unchanged)
+    cases = []
+    base2 = C.g2_mul(C.g2, rs())
+    for k in [0, 1, 2, P.r - 1, P.r, rs(), rs(), (1 << 256) - 1]:
+        cases.append({"p": g2b(base2), "k": h(int(k % (1 << 256)).to_bytes(32, "big")), "out": g2b(C.g2_mul(base2, k))})
+    cases.append({"p": g2b(None), "k": h(int(rs()).to_bytes(32, "big")), "out": g2b(None)})
+    out["g2_mul"] = cases
+    Q2 = C.g2_mul(C.g2, rs())
+    out["g2_add"] = [{"p": g2b(a_), "q": g2b(b_), "out": g2b(C.g2_add(a_, b_))}
+                     for (a_, b_) in [(base2, Q2), (base2, base2), (base2, C.g2_neg(base2)), (None, Q2), (Q2, None)]]
+
+    # ---- Gt.Mul / Gt.Inverse / Gt.Exp on a pairing value (order r) and on a raw Miller-loop value (not cyclotomic)
+    p1, p2 = C.g1_mul(C.g1, rs()), C.g2_mul(C.g2, rs())
+    e_can = pr.final_exp(pr.miller_textbook([(p1, p2)]))
+    e_raw = pr.miller_projective([(p1, p2)])
+    cases = []
+    for el in (e_can, e_raw):
+        for k in [0, 1, 2, 3, P.r - 1, P.r, rs(), (1 << 256) - 1]:
+            cases.append({"a": gtb(el), "k": h(int(k).to_bytes(32, "big")), "out": gtb(T.f12_pow(el, k))})
+    out["gt_exp"] = cases
+    out["gt_mul"] = [{"a": gtb(x_), "b": gtb(y_), "out": gtb(T.f12_mul(x_, y_))}
+                     for (x_, y_) in [(e_can, e_raw), (e_raw, e_raw), (e_can, T.f12_one), (e_can, T.f12_inv(e_can))]]
+    out["gt_inv"] = [{"a": gtb(x_), "out": gtb(T.f12_inv(x_))} for x_ in (e_can, e_raw, T.f12_one)]
     return out
 
 

@@ -137,3 +137,63 @@ def test_bad_encoding_is_an_error(m):
         c.G1MulBatch(bad, (1).to_bytes(32, "big"), 1)
     with pytest.raises(m.B200Error):
         m.check(m.load().b200_fp_bytes(99))
+
+
+# ---- the callers next to the hot path -------------------------------------------------------------
+@pytest.mark.parametrize("cid", CURVE_IDS)
+def test_g2_mul_add_golden(m, cid):
+    """driver.G2.Mul / G2.Add (reference driver/math.go:307-310) against the oracle's affine results, bit-exact."""
+    c = m.Curves[cid]
+    v = load_vectors(cid)
+    for case in v["g2_mul"]:
+        p = c.NewG2FromBytes(bytes.fromhex(case["p"]))
+        k = c.NewZrFromBytes(bytes.fromhex(case["k"]))
+        before = p.Bytes()
+        assert p.Mul(k).Bytes().hex() == case["out"]
+        assert p.Bytes() == before                          # receiver untouched (math_test.go:399-420 relies on it)
+    n = len(v["g2_mul"])
+    out = c.G2MulBatch(b"".join(bytes.fromhex(x["p"]) for x in v["g2_mul"]),
+                       b"".join(bytes.fromhex(x["k"]) for x in v["g2_mul"]), n)
+    assert out.hex() == "".join(x["out"] for x in v["g2_mul"])
+    for case in v["g2_add"]:
+        p = c.NewG2FromBytes(bytes.fromhex(case["p"]))
+        p.Add(c.NewG2FromBytes(bytes.fromhex(case["q"])))
+        assert p.Bytes().hex() == case["out"]
+
+
+@pytest.mark.parametrize("cid", CURVE_IDS)
+def test_gt_ops_golden(m, cid):
+    """driver.Gt.Exp / Mul / Inverse (reference driver/math.go:339-360) on a pairing value and on a raw Miller value."""
+    c = m.Curves[cid]
+    v = load_vectors(cid)
+    for case in v["gt_exp"]:
+        a = c.NewGtFromBytes(bytes.fromhex(case["a"]))
+        # exponents are used as given (32 bytes), not reduced mod r: hand the raw bytes to the batch call
+        assert c.GtExpBatch(a.Bytes(), bytes.fromhex(case["k"]), 1).hex() == case["out"]
+    n = len(v["gt_exp"])
+    out = c.GtExpBatch(b"".join(bytes.fromhex(x["a"]) for x in v["gt_exp"]),
+                       b"".join(bytes.fromhex(x["k"]) for x in v["gt_exp"]), n)
+    assert out.hex() == "".join(x["out"] for x in v["gt_exp"])
+    for case in v["gt_mul"]:
+        a = c.NewGtFromBytes(bytes.fromhex(case["a"]))
+        a.Mul(c.NewGtFromBytes(bytes.fromhex(case["b"])))
+        assert a.Bytes().hex() == case["out"]
+    for case in v["gt_inv"]:
+        a = c.NewGtFromBytes(bytes.fromhex(case["a"]))
+        a.Inverse()
+        assert a.Bytes().hex() == case["out"]
+
+
+def test_gt_exp_bilinearity(m):
+    """e(aP, bQ) == e(P, Q)^(ab) and GenGt^r == 1 (reference math_test.go:399-420, 900-902) through Gt.Exp."""
+    import random
+    for cid in CURVE_IDS:
+        c = m.Curves[cid]
+        rnd = random.Random(77 + cid)
+        a, b = rnd.randrange(1, c.order), rnd.randrange(1, c.order)
+        za, zb = c.NewZrFromInt(a), c.NewZrFromInt(b)
+        lhs = c.FExp(c.Pairing(c.GenG2.Mul(zb), c.GenG1.Mul(za)))
+        rhs = c.GenGt.Exp(c.NewZrFromInt(a * b % c.order))
+        assert lhs.Bytes() == rhs.Bytes()
+        # Zr.Bytes() reduces (GroupOrder -> 0), so the exponent r itself goes through the batch call as raw bytes
+        assert c.GtExpBatch(c.GenGt.Bytes(), c.order.to_bytes(32, "big"), 1) == c._gt_one

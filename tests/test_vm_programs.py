@@ -37,6 +37,21 @@ def test_vm_pairing_matches_oracle(vmname):
         assert DR.f12_from_slots(slots, ob) == pr.final_exp(pr.miller_textbook(pairs))
 
 
+@pytest.mark.parametrize("vmname", ['BLS381', 'BN254', 'BLS377'])
+def test_vm_gt_exp_matches_oracle(vmname):
+    """Gt.Exp ladder (F12_SQR + predicated F12_MULP) against the oracle's Fp12 pow, on a non-cyclotomic element too."""
+    ctx, pr = make_ctx(vmname)
+    T, P = pr.T, pr.P
+    rnd = random.Random(5)
+    for k in (0, 1, 2, rnd.randrange(1 << 64), P.r - 1):
+        g = [(rnd.randrange(P.p), rnd.randrange(P.p)) for _ in range(6)]
+        slots = [(0, 0)] * ctx.nslots
+        slots[0:6] = g
+        ob = DR.gt_exp(ctx, slots, k)
+        f = ((g[0], g[2], g[4]), (g[1], g[3], g[5]))
+        assert DR.f12_from_slots(slots, ob) == T.f12_pow(f, k)
+
+
 def test_program_budgets():
     from mathlib_b200.vm import programs as PR
     for name in PR.CURVES:

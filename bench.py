@@ -483,6 +483,22 @@ def run_extra(m, lib, dev, stream, torch):
         raise RuntimeError("BBS-style verification verdicts are wrong")
     out["config4_bls12_381_bbs_verify_12500_per_gpu_share"] = {"ms": ms, "verifications_per_s": n / ms * 1e3,
                                                                "what": "Mul2 -> Pairing2+FExp -> IsUnity, device resident"}
+    # SURVEY 8(f) row 3, the callers next to the hot path: Gt.Exp and G2.Mul batches on BLS12-381 (device resident)
+    c = m.Curves[5]
+    n = 16384
+    gt = torch.frombuffer(bytearray(c.GenGt.Bytes() * n), dtype=torch.uint8).to(dev)
+    ksr = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ksr[:, 0] &= 0x3F
+    d_kr = torch.from_numpy(ksr.reshape(-1)).to(dev)
+    o = torch.empty(n * c.GtByteSize, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: m.check(lib.b200_gt_exp_batch(5, n, gt.data_ptr(), d_kr.data_ptr(), o.data_ptr(), m.DEVICE_PTRS)),
+               reps=2)
+    out["next_gt_exp_bls12_381_16384"] = {"ms": ms, "exps_per_s": n / ms * 1e3}
+    g2 = torch.frombuffer(bytearray(c.GenG2.Bytes() * n), dtype=torch.uint8).to(dev)
+    o2 = torch.empty(n * c.G2ByteSize, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: m.check(lib.b200_g2_mul_batch(5, n, g2.data_ptr(), d_kr.data_ptr(), o2.data_ptr(), m.DEVICE_PTRS)),
+               reps=2)
+    out["next_g2_mul_bls12_381_16384"] = {"ms": ms, "muls_per_s": n / ms * 1e3}
     return out
 
 

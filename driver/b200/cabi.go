@@ -92,3 +92,35 @@ func g1Sum(curve int, n int, pts []byte, g1Size int) []byte {
 	check("g1 sum", C.b200_g1_sum(C.int(curve), C.size_t(n), ptr(pts), ptr(out), 0))
 	return out
 }
+
+// ---- callers next to the hot path (SURVEY 8f-3) ----
+
+func g2MulBatch(curve int, n int, pts, scalars []byte, flags uint32) []byte {
+	out := make([]byte, len(pts))
+	check("g2 mul", C.b200_g2_mul_batch(C.int(curve), C.size_t(n), ptr(pts), ptr(scalars), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func g2Sum(curve int, n int, pts []byte, g2Size int) []byte {
+	out := make([]byte, g2Size)
+	check("g2 sum", C.b200_g2_sum(C.int(curve), C.size_t(n), ptr(pts), ptr(out), 0))
+	return out
+}
+
+func gtMulBatch(curve int, n int, a, b []byte, flags uint32) []byte {
+	out := make([]byte, len(a))
+	check("gt mul", C.b200_gt_mul_batch(C.int(curve), C.size_t(n), ptr(a), ptr(b), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func gtInvBatch(curve int, n int, a []byte, flags uint32) []byte {
+	out := make([]byte, len(a))
+	check("gt inverse", C.b200_gt_inv_batch(C.int(curve), C.size_t(n), ptr(a), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func gtExpBatch(curve int, n int, a, scalars []byte, flags uint32) []byte {
+	out := make([]byte, len(a))
+	check("gt exp", C.b200_gt_exp_batch(C.int(curve), C.size_t(n), ptr(a), ptr(scalars), ptr(out), C.uint32_t(flags)))
+	return out
+}

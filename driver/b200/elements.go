@@ -71,8 +71,8 @@ func (g *G1) Sub(a driver.G1) {
 	g.Add(t)
 }
 
-// G2 implements driver.G2 (reference driver/math.go:299-329).  Only serialisation is on the hot path; G2 group
-// operations are the "next" row 8f-3 and panic until their kernels exist.
+// G2 implements driver.G2 (reference driver/math.go:299-329).  Group operations are the n == 1 (Mul) / n == 2 (Add)
+// cases of b200_g2_mul_batch / b200_g2_sum (SURVEY 8f-3).
 type G2 struct {
 	c   *Curve
 	raw []byte // X.A1 || X.A0 || Y.A1 || Y.A0
@@ -84,10 +84,37 @@ func (g *G2) String() string          { return hex.EncodeToString(g.raw) }
 func (g *G2) Copy() driver.G2         { return &G2{c: g.c, raw: append([]byte(nil), g.raw...)} }
 func (g *G2) Clone(a driver.G2)       { g.raw = append(g.raw[:0], a.(*G2).raw...) }
 func (g *G2) Equals(a driver.G2) bool { return bytes.Equal(g.raw, a.(*G2).raw) }
-func (g *G2) Mul(a driver.Zr) driver.G2 { panic("b200: G2.Mul kernel is a next-round row (SURVEY 8f-3)") }
-func (g *G2) Add(a driver.G2)           { panic("b200: G2.Add kernel is a next-round row (SURVEY 8f-3)") }
-func (g *G2) Sub(a driver.G2)           { panic("b200: G2.Sub kernel is a next-round row (SURVEY 8f-3)") }
-func (g *G2) Affine()                   {}
+func (g *G2) Affine()                 {}
+
+// Mul returns [a]g; the receiver is untouched (reference driver/math.go:307).
+func (g *G2) Mul(a driver.Zr) driver.G2 {
+	return &G2{c: g.c, raw: g2MulBatch(g.c.id, 1, g.raw, a.Bytes(), 0)}
+}
+
+// Add / Sub mutate the receiver (reference driver/math.go:310-313).
+func (g *G2) Add(a driver.G2) {
+	g.raw = g2Sum(g.c.id, 2, append(append([]byte(nil), g.raw...), a.(*G2).raw...), g.c.g2Size())
+}
+func (g *G2) Sub(a driver.G2) {
+	// -(x, y) = (x, -y): negate both Fp components of Y (bytes 2n..4n hold Y.A1 || Y.A0)
+	t := a.Copy().(*G2)
+	n := g.c.fpBytes
+	zero := true
+	for i, b := range t.raw {
+		if (i == 0 && b&^0x40 != 0) || (i != 0 && b != 0) {
+			zero = false
+		}
+	}
+	if !zero {
+		for k := 2; k < 4; k++ {
+			y := new(big.Int).SetBytes(t.raw[k*n : (k+1)*n])
+			y.Sub(fieldModulus(g.c.id), y)
+			y.Mod(y, fieldModulus(g.c.id))
+			y.FillBytes(t.raw[k*n : (k+1)*n])
+		}
+	}
+	g.Add(t)
+}
 
 // Gt implements driver.Gt (reference driver/math.go:339-360).
 type Gt struct {
@@ -106,6 +133,11 @@ func (g *Gt) IsUnity() bool {
 	}
 	return true
 }
-func (g *Gt) Inverse()                    { panic("b200: Gt.Inverse kernel is a next-round row (SURVEY 8f-3)") }
-func (g *Gt) Mul(a driver.Gt)             { panic("b200: Gt.Mul kernel is a next-round row (SURVEY 8f-3)") }
-func (g *Gt) Exp(z driver.Zr) driver.Gt   { panic("b200: Gt.Exp kernel is a next-round row (SURVEY 8f-3)") }
+
+// Inverse / Mul mutate the receiver, Exp returns a fresh value (reference driver/math.go:344-359); n == 1 cases of
+// b200_gt_inv_batch / b200_gt_mul_batch / b200_gt_exp_batch (SURVEY 8f-3).
+func (g *Gt) Inverse()        { g.raw = gtInvBatch(g.c.id, 1, g.raw, 0) }
+func (g *Gt) Mul(a driver.Gt) { g.raw = gtMulBatch(g.c.id, 1, g.raw, a.(*Gt).raw, 0) }
+func (g *Gt) Exp(z driver.Zr) driver.Gt {
+	return &Gt{c: g.c, raw: gtExpBatch(g.c.id, 1, g.raw, z.Bytes(), 0)}
+}

@@ -78,6 +78,34 @@ struct Curve {
         check("multi scalar mul", b200_g1_msm(id, a.size(), pts.data(), ks.data(), r.raw.data(), 0));
         return r;
     }
+    // callers next to the hot path (reference driver/math.go:307-310, 344-359)
+    G2 g2Mul(const G2& p, const Zr& a) const {
+        G2 r; r.raw.resize(g2Size());
+        check("g2 mul", b200_g2_mul_batch(id, 1, p.raw.data(), a.be32.data(), r.raw.data(), 0));
+        return r;
+    }
+    G2 g2Add(const G2& p, const G2& q) const {
+        Bytes two(p.raw);
+        two.insert(two.end(), q.raw.begin(), q.raw.end());
+        G2 r; r.raw.resize(g2Size());
+        check("g2 add", b200_g2_sum(id, 2, two.data(), r.raw.data(), 0));
+        return r;
+    }
+    Gt gtExp(const Gt& a, const Zr& k) const {
+        Gt r; r.raw.resize(gtSize());
+        check("gt exp", b200_gt_exp_batch(id, 1, a.raw.data(), k.be32.data(), r.raw.data(), 0));
+        return r;
+    }
+    Gt gtMul(const Gt& a, const Gt& b) const {
+        Gt r; r.raw.resize(gtSize());
+        check("gt mul", b200_gt_mul_batch(id, 1, a.raw.data(), b.raw.data(), r.raw.data(), 0));
+        return r;
+    }
+    Gt gtInverse(const Gt& a) const {
+        Gt r; r.raw.resize(gtSize());
+        check("gt inverse", b200_gt_inv_batch(id, 1, a.raw.data(), r.raw.data(), 0));
+        return r;
+    }
     // batch entry points: contiguous slabs
     Bytes pairing2Batch(size_t n, const Bytes& g1a, const Bytes& g2a, const Bytes& g1b, const Bytes& g2b, unsigned flags) const {
         Bytes out((flags & B200_OUT_UNITY_ONLY) ? n : n * gtSize());

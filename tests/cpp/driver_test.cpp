@@ -44,6 +44,13 @@ int main(int argc, char** argv) {
         (void)p1a.mul(e);
         printf("receiver_unchanged %d\n", (int)before.equals(p1a));
         printf("msm %s\n", hex(c.multiScalarMul({p1a, p1b}, {e, f}).bytes()).c_str());
+        // bilinearity through the neighbouring ops (math_test.go:399-420): e([e]P, [f]Q) == e(P, Q)^e^f, and a * a^-1 == 1
+        Gt base = c.fexp(c.pairing(p2a, p1a));
+        Gt lhs = c.fexp(c.pairing(c.g2Mul(p2a, f), p1a.mul(e)));
+        Gt rhs = c.gtExp(c.gtExp(base, e), f);
+        printf("bilinear %d\n", (int)lhs.equals(rhs));
+        printf("inverse_ok %d\n", (int)c.gtMul(base, c.gtInverse(base)).isUnity());
+        printf("g2_add_is_double %d\n", (int)(c.g2Add(p2a, p2a).raw == c.g2Mul(p2a, Zr{unhex("0000000000000000000000000000000000000000000000000000000000000002")}).raw));
         // error behaviour: bad curve id throws
         bool threw = false;
         try { Curve bad(99); } catch (const std::runtime_error&) { threw = true; }

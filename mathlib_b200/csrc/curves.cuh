@@ -20,13 +20,17 @@ struct CurveConsts {
     uint32_t frob3[10 * N]; // gamma_{3,i} = xi^(i(p^3-1)/6)
     uint32_t p2[31 * 2 * N]; // k * p^2, k = 0..30, 2N words each (lazy-reduction offsets, vm.cuh)
     uint32_t r3[N];          // R^3 mod p (binary inversion fix-up)
+    uint32_t glv_lambda[4];  // BLS12 G1 endomorphism eigenvalue lambda = x^2 - 1 (zeros: no GLV)
+    uint32_t glv_m[5];       // floor(2^256 / lambda)
+    uint32_t glv_beta[N];    // cube root of unity with [lambda](X, Y) = (beta X, Y), Montgomery
 };
 
 #define B200_DEFINE_CONSTS(NAME, NL)                                                        \
     static const CurveConsts<NL> H_##NAME = {NAME##_P, NAME##_ONE, NAME##_R2, NAME##_B,     \
                                              NAME##_B3, NAME##_BTW, NAME##_ORDER,           \
                                              NAME##_FROB1, NAME##_FROB2, NAME##_FROB3, NAME##_P2, \
-                                             NAME##_R3};
+                                             NAME##_R3, NAME##_GLV_LAMBDA, NAME##_GLV_M,    \
+                                             NAME##_GLV_BETA};
 
 B200_DEFINE_CONSTS(BN254, 8)
 B200_DEFINE_CONSTS(BLS381, 12)
@@ -38,7 +42,8 @@ B200_DEFINE_CONSTS(BLS377, 12)
                                                         NAME##_B, NAME##_B3, NAME##_BTW,    \
                                                         NAME##_ORDER, NAME##_FROB1,         \
                                                         NAME##_FROB2, NAME##_FROB3, NAME##_P2,      \
-                                                        NAME##_R3};
+                                                        NAME##_R3, NAME##_GLV_LAMBDA,       \
+                                                        NAME##_GLV_M, NAME##_GLV_BETA};
 B200_DEFINE_DCONSTS(BN254, 8)
 B200_DEFINE_DCONSTS(BLS381, 12)
 B200_DEFINE_DCONSTS(BLS377, 12)

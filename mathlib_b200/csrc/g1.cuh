@@ -143,19 +143,113 @@ struct G1Ops {
     // scalar: 8 little-endian 32-bit words (any 256-bit value; [k]P = [k mod r]P in the r-torsion)
     static B200_HD int scalar_bit(const uint32_t* k, int i) { return (k[i >> 5] >> (i & 31)) & 1; }
 
+    // ---- GLV (BLS12 curves): k = k1 + k2*lambda over the integers with lambda = x^2 - 1 (lambda^2 + lambda + 1 = 0 mod
+    // r) and [lambda](X, Y) = (beta X, Y) on the order-r subgroup, so [k]P = [k1]P + [k2]phi(P) with ~128-bit halves: half
+    // the doublings.  P + phi(P) = -phi^2(P) = (-(X + beta X), -Y) is free, so the joint ladder adds one of three AFFINE
+    // points per step.  (gnark's ScalarMultiplication -- what the reference forwards to -- is a GLV ladder too; like it,
+    // this assumes subgroup points, which is what mathlib's deserialisers guarantee.)
+    // k2 = ((k >> 120) * floor(2^256/lambda)) >> 136 under-estimates floor(k/lambda) by at most 3, so k1 = k - k2*lambda
+    // is in [0, 4*lambda): both halves fit 5 words for any 256-bit k.
+    static B200_HD_NOINLINE void glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k) {
+        const uint32_t* lam = C::K().glv_lambda;
+        const uint32_t* M = C::K().glv_m;
+        uint32_t kh[5], prod[11];
+        for (int j = 0; j < 5; j++) kh[j] = (k[3 + j] >> 24) | (j + 4 < 8 ? (k[4 + j] << 8) : 0u);
+        for (int j = 0; j < 11; j++) prod[j] = 0;
+        for (int i = 0; i < 5; i++) {
+            uint64_t carry = 0;
+            for (int j = 0; j < 5; j++) {
+                uint64_t t = (uint64_t)kh[i] * M[j] + prod[i + j] + carry;
+                prod[i + j] = (uint32_t)t;
+                carry = t >> 32;
+            }
+            prod[i + 5] = (uint32_t)carry;
+        }
+        for (int j = 0; j < 5; j++) k2[j] = (prod[4 + j] >> 8) | (prod[5 + j] << 24);
+        uint32_t t5[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < 5; i++) {
+            uint64_t carry = 0;
+            for (int j = 0; j < 4 && i + j < 5; j++) {
+                uint64_t t = (uint64_t)k2[i] * lam[j] + t5[i + j] + carry;
+                t5[i + j] = (uint32_t)t;
+                carry = t >> 32;
+            }
+            if (i == 0) t5[4] = (uint32_t)carry;          // rows i >= 1 end at or beyond word 4: their carry is 2^160 * ...
+        }
+        uint64_t borrow = 0;
+        for (int j = 0; j < 5; j++) {
+            uint64_t d = (uint64_t)k[j] - t5[j] - borrow;
+            k1[j] = (uint32_t)d;
+            borrow = (d >> 32) & 1;
+        }
+    }
+    struct GlvTable { E x1, x2, x3, y, ny; };       // P = (x1, y), phi(P) = (x2, y), P + phi(P) = (x3, -y)
+    static B200_HD_NOINLINE void glv_table(GlvTable& t, const Aff& base) {
+        E beta;
+        const uint32_t* bw = C::K().glv_beta;
+        for (int i = 0; i < N; i++) beta.l[i] = bw[i];
+        t.x1 = base.x;
+        t.y = base.y;
+        F::mulx(t.x2, base.x, beta);
+        F::add(t.x3, t.x1, t.x2);
+        F::neg(t.x3, t.x3);
+        F::neg(t.ny, base.y);
+    }
+    static B200_HD_NOINLINE void glv_step(Pt& acc, const GlvTable& t, uint32_t b) {    // b in 1..3
+        Aff s;
+        s.x = b == 1 ? t.x1 : (b == 2 ? t.x2 : t.x3);
+        s.y = b == 3 ? t.ny : t.y;
+        madd(acc, s);
+    }
+    static B200_HD uint32_t glv_bits(const uint32_t* k1, const uint32_t* k2, int i) {
+        return ((k1[i >> 5] >> (i & 31)) & 1u) | (((k2[i >> 5] >> (i & 31)) & 1u) << 1);
+    }
+
     static B200_HD void scalar_mul(Pt& acc, const Aff& base, const uint32_t* k) {
         set_inf(acc);
+        if (C::FAMILY == FAMILY_BLS12) {
+            uint32_t k1[5], k2[5];
+            glv_split(k1, k2, k);
+            GlvTable t;
+            glv_table(t, base);
+            int top = 159;
+            while (top >= 0 && !glv_bits(k1, k2, top)) top--;
+            for (int i = top; i >= 0; i--) {
+                dbl(acc);
+                const uint32_t b = glv_bits(k1, k2, i);
+                if (b) glv_step(acc, t, b);
+            }
+            return;
+        }
         for (int i = 255; i >= 0; i--) {
             dbl(acc);
             if (scalar_bit(k, i)) madd(acc, base);
         }
     }
-    // [e]P + [f]Q, Strauss-Shamir with a joint 1-bit window
+    // [e]P + [f]Q.  BLS12: two GLV tables, one shared doubling chain of ~130 steps, at most two mixed additions per step.
+    // BN254: Strauss-Shamir with a joint 1-bit window.
     static B200_HD void scalar_mul2(Pt& acc, const Aff& P, const uint32_t* e, const Aff& Q, const uint32_t* f) {
+        set_inf(acc);
+        if (C::FAMILY == FAMILY_BLS12) {
+            uint32_t e1[5], e2[5], f1[5], f2[5];
+            glv_split(e1, e2, e);
+            glv_split(f1, f2, f);
+            GlvTable tp, tq;
+            glv_table(tp, P);
+            glv_table(tq, Q);
+            int top = 159;
+            while (top >= 0 && !(glv_bits(e1, e2, top) | glv_bits(f1, f2, top))) top--;
+            for (int i = top; i >= 0; i--) {
+                dbl(acc);
+                const uint32_t bp = glv_bits(e1, e2, i), bq = glv_bits(f1, f2, i);
+                if (bp) glv_step(acc, tp, bp);
+                if (bq) glv_step(acc, tq, bq);
+            }
+            return;
+        }
         Pt pq;
         from_affine(pq, P);
         madd(pq, Q);
-        set_inf(acc);
         for (int i = 255; i >= 0; i--) {
             dbl(acc);
             int b = scalar_bit(e, i) | (scalar_bit(f, i) << 1);

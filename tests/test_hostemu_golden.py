@@ -31,6 +31,32 @@ def test_g1_ops(hostemu, cid):
         assert rc == 0 and out.raw.hex() == case["out"]
 
 
+@pytest.mark.parametrize("cid", [4, 5])
+def test_g1_glv_random_scalars(hostemu, cid):
+    """The GLV split k = k1 + k2*lambda of g1.cuh on random and extreme 256-bit scalars (any value < 2^256 is legal at
+    the ABI), against the C++ oracle's plain double-and-add."""
+    import random
+    from oracle import cpu_binding as orc
+    v = load_vectors(cid)
+    ec = EMU_CURVE[cid]
+    base = bytes.fromhex(v["g1_mul"][0]["p"])
+    q = bytes.fromhex(v["g1_mul2"][0]["q"])
+    rnd = random.Random(1234 + cid)
+    ks = [rnd.getrandbits(256) for _ in range(40)] + [rnd.getrandbits(b) for b in (1, 64, 120, 121, 127, 128, 129, 136, 200)]
+    ks += [(1 << 256) - 1, (1 << 255), (1 << 128) - 1, (1 << 128), (1 << 120) - 1, 3]
+    kb = b"".join(k.to_bytes(32, "big") for k in ks)
+    want = orc.g1_mul_batch(cid, len(ks), base * len(ks), kb)
+    out = ctypes.create_string_buffer(96)
+    for i, k in enumerate(ks):
+        assert hostemu.he_g1_op(ec, 0, base, k.to_bytes(32, "big"), None, None, out) == 0
+        assert out.raw == want[96 * i:96 * (i + 1)], hex(k)
+    fs = ks[::-1]
+    want2 = orc.g1_mul2_batch(cid, len(ks), base * len(ks), kb, q * len(ks), b"".join(k.to_bytes(32, "big") for k in fs))
+    for i in range(0, len(ks), 3):
+        assert hostemu.he_g1_op(ec, 1, base, ks[i].to_bytes(32, "big"), q, fs[i].to_bytes(32, "big"), out) == 0
+        assert out.raw == want2[96 * i:96 * (i + 1)]
+
+
 @pytest.mark.parametrize("cid", [1, 4, 5])
 def test_pairing(hostemu, cid):
     v = load_vectors(cid)

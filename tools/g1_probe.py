@@ -4,7 +4,7 @@ import numpy as np, torch
 import mathlib_b200 as m
 lib = m.load(); dev = torch.device("cuda:0")
 lib.b200_set_stream(torch.cuda.current_stream().cuda_stream)
-cid = 5; c = m.Curves[cid]; n = 65536
+cid = int(os.environ.get("CID", "5")); c = m.Curves[cid]; n = int(os.environ.get("N", "65536"))
 rng = np.random.default_rng(1)
 ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); ks[:, 0] &= 0x3F
 d_k = torch.from_numpy(ks.reshape(-1)).to(dev)

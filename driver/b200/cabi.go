@@ -124,3 +124,27 @@ func gtExpBatch(curve int, n int, a, scalars []byte, flags uint32) []byte {
 	check("gt exp", C.b200_gt_exp_batch(C.int(curve), C.size_t(n), ptr(a), ptr(scalars), ptr(out), C.uint32_t(flags)))
 	return out
 }
+
+// ---- point (de)serialisation and validation batches (SURVEY 8f-2) ----
+
+// pointCodec: op 0 decompress, 1 compress, 2 validate; outElem = bytes per output element.
+func pointCodec(curve, g2, op, n int, in []byte, outElem int, flags uint32) []byte {
+	out := make([]byte, n*outElem)
+	var rc C.int
+	switch {
+	case g2 == 0 && op == 0:
+		rc = C.b200_g1_decompress_batch(C.int(curve), C.size_t(n), ptr(in), ptr(out), C.uint32_t(flags))
+	case g2 == 0 && op == 1:
+		rc = C.b200_g1_compress_batch(C.int(curve), C.size_t(n), ptr(in), ptr(out), C.uint32_t(flags))
+	case g2 == 0:
+		rc = C.b200_g1_validate_batch(C.int(curve), C.size_t(n), ptr(in), ptr(out), C.uint32_t(flags))
+	case op == 0:
+		rc = C.b200_g2_decompress_batch(C.int(curve), C.size_t(n), ptr(in), ptr(out), C.uint32_t(flags))
+	case op == 1:
+		rc = C.b200_g2_compress_batch(C.int(curve), C.size_t(n), ptr(in), ptr(out), C.uint32_t(flags))
+	default:
+		rc = C.b200_g2_validate_batch(C.int(curve), C.size_t(n), ptr(in), ptr(out), C.uint32_t(flags))
+	}
+	check("set bytes", rc)
+	return out
+}

@@ -139,11 +139,19 @@ func (c *Curve) NewG1FromBytes(b []byte) driver.G1 {
 	if len(b) != c.g1Size() {
 		panic("failure [invalid G1 length]")
 	}
+	// gnark SetBytes / kilic FromUncompressed reject non-canonical, off-curve and out-of-subgroup points
+	// (reference driver/gurvy/bn254.go:339-347, kilic/bls12-381.go:344-355)
+	if pointCodec(c.id, 0, 2, 1, b, 1, 0)[0] != 1 {
+		panic("set bytes failed [invalid point]")
+	}
 	return &G1{c: c, raw: append([]byte(nil), b...)}
 }
 func (c *Curve) NewG2FromBytes(b []byte) driver.G2 {
 	if len(b) != c.g2Size() {
 		panic("failure [invalid G2 length]")
+	}
+	if pointCodec(c.id, 1, 2, 1, b, 1, 0)[0] != 1 {
+		panic("set bytes failed [invalid point]")
 	}
 	return &G2{c: c, raw: append([]byte(nil), b...)}
 }
@@ -154,10 +162,21 @@ func (c *Curve) NewGtFromBytes(b []byte) driver.Gt {
 	return &Gt{c: c, raw: append([]byte(nil), b...)}
 }
 
-// Compressed encodings need a square root: deserialisation kernels are the "next" row of the scope table
-// (SURVEY 8f-2); until then these two panic like an invalid encoding would.
-func (c *Curve) NewG1FromCompressed(b []byte) driver.G1 { panic("b200: compressed G1 decoding not implemented") }
-func (c *Curve) NewG2FromCompressed(b []byte) driver.G2 { panic("b200: compressed G2 decoding not implemented") }
+// NewG1FromCompressed / NewG2FromCompressed decompress, and check curve and subgroup membership, on the device
+// (SURVEY 8f-2; reference driver/gurvy/bn254.go:359-377, kilic/bls12-381.go:370-394).  A bad encoding panics with the
+// reference's message style.
+func (c *Curve) NewG1FromCompressed(b []byte) driver.G1 {
+	if len(b) != c.fpBytes {
+		panic("failure [invalid compressed G1 length]")
+	}
+	return &G1{c: c, raw: pointCodec(c.id, 0, 0, 1, b, c.g1Size(), 0)}
+}
+func (c *Curve) NewG2FromCompressed(b []byte) driver.G2 {
+	if len(b) != 2*c.fpBytes {
+		panic("failure [invalid compressed G2 length]")
+	}
+	return &G2{c: c, raw: pointCodec(c.id, 1, 0, 1, b, c.g2Size(), 0)}
+}
 
 func (c *Curve) HashToZr(data []byte) driver.Zr {
 	digest := sha256.Sum256(data) // reference driver/common/curve.go:86-92

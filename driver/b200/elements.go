@@ -19,7 +19,7 @@ type G1 struct {
 }
 
 func (g *G1) Bytes() []byte      { return append([]byte(nil), g.raw...) }
-func (g *G1) Compressed() []byte { panic("b200: compressed G1 encoding not implemented (SURVEY 8f-2)") }
+func (g *G1) Compressed() []byte { return pointCodec(g.c.id, 0, 1, 1, g.raw, g.c.fpBytes, 0) }
 func (g *G1) String() string     { return hex.EncodeToString(g.raw) }
 func (g *G1) Copy() driver.G1    { return &G1{c: g.c, raw: append([]byte(nil), g.raw...)} }
 func (g *G1) Clone(a driver.G1)  { g.raw = append(g.raw[:0], a.(*G1).raw...) }
@@ -79,7 +79,7 @@ type G2 struct {
 }
 
 func (g *G2) Bytes() []byte           { return append([]byte(nil), g.raw...) }
-func (g *G2) Compressed() []byte      { panic("b200: compressed G2 encoding not implemented (SURVEY 8f-2)") }
+func (g *G2) Compressed() []byte      { return pointCodec(g.c.id, 1, 1, 1, g.raw, 2*g.c.fpBytes, 0) }
 func (g *G2) String() string          { return hex.EncodeToString(g.raw) }
 func (g *G2) Copy() driver.G2         { return &G2{c: g.c, raw: append([]byte(nil), g.raw...)} }
 func (g *G2) Clone(a driver.G2)       { g.raw = append(g.raw[:0], a.(*G2).raw...) }

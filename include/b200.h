@@ -58,6 +58,7 @@ extern "C" {
                                     memory, one-time cost of c*(W-1) doublings per point); MSMs against the handle then
                                     skip the Horner tail.  Ignored (plain bases kept) when the table would exceed 1/4 of
                                     the device memory. */
+#define B200_NO_SUBGROUP_CHECK 0x40u /* decompress / validate: skip the [r]P == O test (on-curve only) */
 
 /* error codes */
 #define B200_OK 0
@@ -123,6 +124,21 @@ int b200_g2_sum(int curve, size_t n, const void* g2_pts, void* out, uint32_t fla
 int b200_gt_mul_batch(int curve, size_t n, const void* gt_a, const void* gt_b, void* gt_out, uint32_t flags);
 int b200_gt_inv_batch(int curve, size_t n, const void* gt_a, void* gt_out, uint32_t flags);
 int b200_gt_exp_batch(int curve, size_t n, const void* gt_a, const void* scalars_be32, void* gt_out, uint32_t flags);
+
+/* ---- point (de)serialisation and validation for whole batches ----
+   NewG1FromCompressed / NewG2FromCompressed (reference driver/gurvy/bn254.go:359-377, bls12381/bls12-381.go:551-569,
+   kilic/bls12-381.go:370-394): compressed -> uncompressed Bytes() (or MONT limbs with B200_OUT_MONT).  A coordinate >= p,
+   an x with no point, wrong flag bits, or (unless B200_NO_SUBGROUP_CHECK) a point outside the order-r subgroup fails the
+   call with B200_ERR_ENCODING, as gnark's SetBytes / kilic's FromCompressed fail. */
+int b200_g1_decompress_batch(int curve, size_t n, const void* compressed, void* out, uint32_t flags);
+int b200_g2_decompress_batch(int curve, size_t n, const void* compressed, void* out, uint32_t flags);
+/* G1.Compressed / G2.Compressed (reference bn254.go:82-86,167-171, bls12381/bls12-381.go:292-296,379-383, kilic/bls12-381.go:81-85,159-163). */
+int b200_g1_compress_batch(int curve, size_t n, const void* pts, void* compressed_out, uint32_t flags);
+int b200_g2_compress_batch(int curve, size_t n, const void* pts, void* compressed_out, uint32_t flags);
+/* The checks of NewG1FromBytes / NewG2FromBytes (reference bn254.go:339-357, kilic/bls12-381.go:344-368): one verdict
+   byte per point, 1 = canonical coordinates, on the curve and (unless B200_NO_SUBGROUP_CHECK) in the subgroup. */
+int b200_g1_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
+int b200_g2_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 
 /* Number of kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
 uint64_t b200_launch_count(void);

@@ -106,6 +106,32 @@ struct Curve {
         check("gt inverse", b200_gt_inv_batch(id, 1, a.raw.data(), r.raw.data(), 0));
         return r;
     }
+    // (de)serialisation with the reference's checks (driver/gurvy/bn254.go:339-377): throws on a bad encoding
+    G1 newG1FromCompressed(const Bytes& b) const {
+        G1 r{this, Bytes(g1Size())};
+        check("set bytes", b200_g1_decompress_batch(id, 1, b.data(), r.raw.data(), 0));
+        return r;
+    }
+    G2 newG2FromCompressed(const Bytes& b) const {
+        G2 r; r.raw.resize(g2Size());
+        check("set bytes", b200_g2_decompress_batch(id, 1, b.data(), r.raw.data(), 0));
+        return r;
+    }
+    Bytes g1Compressed(const G1& p) const {
+        Bytes out(fp);
+        check("compress", b200_g1_compress_batch(id, 1, p.raw.data(), out.data(), 0));
+        return out;
+    }
+    Bytes g2Compressed(const G2& p) const {
+        Bytes out(2 * (size_t)fp);
+        check("compress", b200_g2_compress_batch(id, 1, p.raw.data(), out.data(), 0));
+        return out;
+    }
+    bool g1IsValid(const G1& p) const {
+        unsigned char ok = 0;
+        check("validate", b200_g1_validate_batch(id, 1, p.raw.data(), &ok, 0));
+        return ok == 1;
+    }
     // batch entry points: contiguous slabs
     Bytes pairing2Batch(size_t n, const Bytes& g1a, const Bytes& g2a, const Bytes& g1b, const Bytes& g2b, unsigned flags) const {
         Bytes out((flags & B200_OUT_UNITY_ONLY) ? n : n * gtSize());

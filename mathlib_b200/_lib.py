@@ -17,6 +17,7 @@ OUT_MONT = 0x4
 OUT_UNITY_ONLY = 0x8
 DEVICE_PTRS = 0x10
 BASES_TABLES = 0x20
+NO_SUBGROUP_CHECK = 0x40
 
 ERR_CUDA, ERR_ARG, ERR_ENCODING, ERR_NOGPU = -1, -2, -3, -4
 
@@ -45,6 +46,12 @@ PROTOTYPES = {
     "b200_gt_mul_batch": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
     "b200_gt_inv_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
     "b200_gt_exp_batch": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
+    "b200_g1_decompress_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g2_decompress_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g1_compress_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g2_compress_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g1_validate_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g2_validate_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
     "b200_launch_count": (_u64, []),
 }
 

@@ -561,10 +561,10 @@ static int elementwise_batch(int curve, size_t n, std::vector<Piece> ins, void* 
     for (auto& p : ins)
         if (!p.host) return fail(B200_ERR_ARG, "null buffer");
     const CurveVTable* vt = ci.vt;
-    const uint32_t kf = kernel_flags(flags) & ~(B200_FEXP | B200_OUT_UNITY_ONLY);
+    const uint32_t kf = (kernel_flags(flags) & ~(B200_FEXP | B200_OUT_UNITY_ONLY)) | (flags & B200_NO_SUBGROUP_CHECK);
     for (auto& p : ins)
         if (p.elem != 32) p.elem *= (size_t)vt->fp_bytes;          // sizes are given in Fp units except 32-byte scalars
-    const size_t osz = out_fp_mult * (size_t)vt->fp_bytes;
+    const size_t osz = out_fp_mult ? out_fp_mult * (size_t)vt->fp_bytes : 1;      // 0: one verdict byte per item
     if (flags & B200_DEVICE_PTRS) {
         int dev = current_device();
         CU(cudaSetDevice(dev));
@@ -617,6 +617,36 @@ int b200_g2_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags)
     CU(cudaStreamSynchronize(w.stream));
     if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
     return 0;
+}
+
+// op 0 decompress, 1 compress, 2 validate (launch.cuh: point_codec)
+static int point_codec_batch(int curve, int g2, int op, size_t n, const void* in, void* out, uint32_t flags) {
+    const size_t unc = g2 ? 4 : 2, cmp = g2 ? 2 : 1;
+    if ((op == 0 && (flags & B200_IN_MONT)) || (op == 1 && (flags & B200_OUT_MONT)))
+        return fail(B200_ERR_ARG, "compressed encodings have no MONT form");
+    return elementwise_batch(curve, n, {{in, op == 0 ? cmp : unc, nullptr}}, out, op == 0 ? unc : (op == 1 ? cmp : 0), flags,
+                             1024, [g2, op](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out,
+                                            uint32_t kf, int* d_err, cudaStream_t s) {
+                                 return vt->point_codec(g2, op, m, p[0].dev, d_out, kf, d_err, s);
+                             });
+}
+int b200_g1_decompress_batch(int curve, size_t n, const void* in, void* out, uint32_t flags) {
+    return point_codec_batch(curve, 0, 0, n, in, out, flags);
+}
+int b200_g2_decompress_batch(int curve, size_t n, const void* in, void* out, uint32_t flags) {
+    return point_codec_batch(curve, 1, 0, n, in, out, flags);
+}
+int b200_g1_compress_batch(int curve, size_t n, const void* in, void* out, uint32_t flags) {
+    return point_codec_batch(curve, 0, 1, n, in, out, flags);
+}
+int b200_g2_compress_batch(int curve, size_t n, const void* in, void* out, uint32_t flags) {
+    return point_codec_batch(curve, 1, 1, n, in, out, flags);
+}
+int b200_g1_validate_batch(int curve, size_t n, const void* in, void* ok_out, uint32_t flags) {
+    return point_codec_batch(curve, 0, 2, n, in, ok_out, flags);
+}
+int b200_g2_validate_batch(int curve, size_t n, const void* in, void* ok_out, uint32_t flags) {
+    return point_codec_batch(curve, 1, 2, n, in, ok_out, flags);
 }
 
 int b200_gt_mul_batch(int curve, size_t n, const void* a, const void* b, void* out, uint32_t flags) {

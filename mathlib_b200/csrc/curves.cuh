@@ -23,6 +23,9 @@ struct CurveConsts {
     uint32_t glv_lambda[4];  // BLS12 G1 endomorphism eigenvalue lambda = x^2 - 1 (zeros: no GLV)
     uint32_t glv_m[5];       // floor(2^256 / lambda)
     uint32_t glv_beta[N];    // cube root of unity with [lambda](X, Y) = (beta X, Y), Montgomery
+    uint32_t ts_exp[N];      // Tonelli-Shanks: (q-1)/2 with p-1 = 2^s q
+    uint32_t ts_z[N];        // g^q for a quadratic non-residue g (Montgomery)
+    uint32_t half_p[N];      // (p-1)/2: y is "lexicographically largest" iff y > half_p
 };
 
 #define B200_DEFINE_CONSTS(NAME, NL)                                                        \
@@ -30,7 +33,7 @@ struct CurveConsts {
                                              NAME##_B3, NAME##_BTW, NAME##_ORDER,           \
                                              NAME##_FROB1, NAME##_FROB2, NAME##_FROB3, NAME##_P2, \
                                              NAME##_R3, NAME##_GLV_LAMBDA, NAME##_GLV_M,    \
-                                             NAME##_GLV_BETA};
+                                             NAME##_GLV_BETA, NAME##_TS_EXP, NAME##_TS_Z, NAME##_HALF_P};
 
 B200_DEFINE_CONSTS(BN254, 8)
 B200_DEFINE_CONSTS(BLS381, 12)
@@ -43,7 +46,8 @@ B200_DEFINE_CONSTS(BLS377, 12)
                                                         NAME##_ORDER, NAME##_FROB1,         \
                                                         NAME##_FROB2, NAME##_FROB3, NAME##_P2,      \
                                                         NAME##_R3, NAME##_GLV_LAMBDA,       \
-                                                        NAME##_GLV_M, NAME##_GLV_BETA};
+                                                        NAME##_GLV_M, NAME##_GLV_BETA,      \
+                                                        NAME##_TS_EXP, NAME##_TS_Z, NAME##_HALF_P};
 B200_DEFINE_DCONSTS(BN254, 8)
 B200_DEFINE_DCONSTS(BLS381, 12)
 B200_DEFINE_DCONSTS(BLS377, 12)
@@ -74,6 +78,7 @@ struct BN254 {
     static B200_HD const uint32_t* one() { return K().one; }
     static B200_HD const uint32_t* r2() { return K().r2; }
     static B200_HD uint32_t inv32() { return BN254_INV32; }
+    static constexpr int TS_S = BN254_TS_S;
 };
 
 struct BLS381 {
@@ -92,6 +97,7 @@ struct BLS381 {
     static B200_HD const uint32_t* one() { return K().one; }
     static B200_HD const uint32_t* r2() { return K().r2; }
     static B200_HD uint32_t inv32() { return BLS381_INV32; }
+    static constexpr int TS_S = BLS381_TS_S;
 };
 
 struct BLS377 {
@@ -110,6 +116,7 @@ struct BLS377 {
     static B200_HD const uint32_t* one() { return K().one; }
     static B200_HD const uint32_t* r2() { return K().r2; }
     static B200_HD uint32_t inv32() { return BLS377_INV32; }
+    static constexpr int TS_S = BLS377_TS_S;
 };
 
 }  // namespace b200

@@ -10,6 +10,7 @@
 #include "msm.cuh"
 #include "pairing_vm.cuh"
 #include "g2.cuh"
+#include "points.cuh"
 
 namespace b200 {
 
@@ -49,6 +50,9 @@ struct CurveVTable {
     cudaError_t (*g2_sum)(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
     cudaError_t (*gt_op)(int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t flags, int* err,
                          cudaStream_t s);
+    // point decompression (op 0) / compression (1) / validation (2) batches, g2 = 0 / 1
+    cudaError_t (*point_codec)(int g2, int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err,
+                               cudaStream_t s);
     // points -> Montgomery affine array (for MSM / resident bases)
     cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
     // resident window tables: tab[w*stride + i] = 2^(c*w) * tab[i]
@@ -218,6 +222,14 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
+    static cudaError_t point_codec(int g2, int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err,
+                                   cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        if (g2) point_codec_kernel<C, 1><<<blocks_for(n, B200_PT_THREADS), B200_PT_THREADS, 0, s>>>(op, n, in, out, flags, err);
+        else point_codec_kernel<C, 0><<<blocks_for(n, B200_PT_THREADS), B200_PT_THREADS, 0, s>>>(op, n, in, out, flags, err);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
     static cudaError_t g2_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
                               cudaStream_t s) {
         if (n == 0) return cudaSuccess;
@@ -306,7 +318,7 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
-                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &msm_points, &msm_tables, &msm};
+                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &point_codec, &msm_points, &msm_tables, &msm};
         return &t;
     }
 };

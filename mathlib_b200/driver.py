@@ -106,6 +106,10 @@ class G1:
     def Copy(self):
         return G1(self.curve, self.raw)
 
+    def Compressed(self):
+        """driver.G1.Compressed (reference driver/gurvy/bn254.go:82-86)."""
+        return self.curve.PointCodecBatch(0, 1, self.raw, 1)
+
     def Equals(self, o):
         return self.raw == o.raw
 
@@ -149,6 +153,10 @@ class G2:
 
     def Copy(self):
         return G2(self.curve, self.raw)
+
+    def Compressed(self):
+        """driver.G2.Compressed (reference driver/gurvy/bn254.go:167-171)."""
+        return self.curve.PointCodecBatch(1, 1, self.raw, 1)
 
     def Equals(self, o):
         return self.raw == o.raw
@@ -237,6 +245,17 @@ class Curve:
         if len(b) != self.G2ByteSize:
             raise ValueError("failure [invalid G2 length %d]" % len(b))
         return G2(self, b)
+
+    def NewG1FromCompressed(self, b):
+        """decompression + on-curve + subgroup checks on the device (reference driver/gurvy/bn254.go:359-367)."""
+        if len(b) != self.CompressedG1ByteSize:
+            raise ValueError("failure [invalid compressed G1 length %d]" % len(b))
+        return G1(self, self.PointCodecBatch(0, 0, b, 1))
+
+    def NewG2FromCompressed(self, b):
+        if len(b) != self.CompressedG2ByteSize:
+            raise ValueError("failure [invalid compressed G2 length %d]" % len(b))
+        return G2(self, self.PointCodecBatch(1, 0, b, 1))
 
     def NewGtFromBytes(self, b):
         if len(b) != self.GtByteSize:
@@ -344,6 +363,17 @@ class Curve:
         out = ctypes.create_string_buffer(max(n * self.GtByteSize, 1))
         check(lib.b200_gt_inv_batch(self.id, n, buf_ptr(a), out, flags))
         return out.raw[:n * self.GtByteSize]
+
+    def PointCodecBatch(self, g2, op, data, n, flags=0):
+        """op 0: compressed -> Bytes(); 1: Bytes() -> compressed; 2: Bytes() -> verdict bytes."""
+        lib = load()
+        unc, cmp_ = (self.G2ByteSize, self.CompressedG2ByteSize) if g2 else (self.G1ByteSize, self.CompressedG1ByteSize)
+        osz = n * (unc if op == 0 else cmp_ if op == 1 else 1)
+        out = ctypes.create_string_buffer(max(osz, 1))
+        fn = [[lib.b200_g1_decompress_batch, lib.b200_g1_compress_batch, lib.b200_g1_validate_batch],
+              [lib.b200_g2_decompress_batch, lib.b200_g2_compress_batch, lib.b200_g2_validate_batch]][g2][op]
+        check(fn(self.id, n, buf_ptr(data), out, flags))
+        return out.raw[:osz]
 
     def MsmBatch(self, pts, scalars, n, flags=0):
         lib = load()

@@ -51,6 +51,9 @@ int main(int argc, char** argv) {
         printf("bilinear %d\n", (int)lhs.equals(rhs));
         printf("inverse_ok %d\n", (int)c.gtMul(base, c.gtInverse(base)).isUnity());
         printf("g2_add_is_double %d\n", (int)(c.g2Add(p2a, p2a).raw == c.g2Mul(p2a, Zr{unhex("0000000000000000000000000000000000000000000000000000000000000002")}).raw));
+        // compressed round trip and validation
+        printf("compress_roundtrip %d\n", (int)(c.newG1FromCompressed(c.g1Compressed(p1a)).raw == p1a.raw &&
+                                                c.newG2FromCompressed(c.g2Compressed(p2a)).raw == p2a.raw && c.g1IsValid(p1a)));
         // error behaviour: bad curve id throws
         bool threw = false;
         try { Curve bad(99); } catch (const std::runtime_error&) { threw = true; }

@@ -169,3 +169,11 @@ extern "C" void he_fp_dot(int curve, int T, const uint32_t* a, const uint32_t* b
     else if (curve == 1) t_dot<BLS381>(T, a, b, o);
     else t_dot<BLS377>(T, a, b, o);
 }
+
+#include "../../mathlib_b200/csrc/points.cuh"
+// point (de)compression / validation, one item (points.cuh: the function the kernel runs per thread)
+extern "C" int he_point_codec(int curve, int g2, int op, const uint8_t* in, uint8_t* out, uint32_t flags) {
+    if (curve == 0) return g2 ? point_codec_item<BN254, 1>(op, in, out, flags) : point_codec_item<BN254, 0>(op, in, out, flags);
+    if (curve == 1) return g2 ? point_codec_item<BLS381, 1>(op, in, out, flags) : point_codec_item<BLS381, 0>(op, in, out, flags);
+    return g2 ? point_codec_item<BLS377, 1>(op, in, out, flags) : point_codec_item<BLS377, 0>(op, in, out, flags);
+}

@@ -29,7 +29,7 @@ def test_cpp_mirror(cid):
     res = dict(line.split(" ", 1) for line in out.stdout.strip().splitlines())
     assert res["pairing2_fexp"] == c["fexp"]
     assert res["mul2_eq_mul_add"] == "1" and res["receiver_unchanged"] == "1" and res["bad_curve_throws"] == "1"
-    assert res["bilinear"] == "1" and res["inverse_ok"] == "1" and res["g2_add_is_double"] == "1"
+    assert res["bilinear"] == "1" and res["inverse_ok"] == "1" and res["g2_add_is_double"] == "1" and res["compress_roundtrip"] == "1"
     g1a, g1b = bytes.fromhex(c["g1a"]), bytes.fromhex(c["g1b"])
     want = orc.g1_mul2_batch(cid, 1, g1a, bytes.fromhex(e), g1b, bytes.fromhex(fs))
     assert res["mul2"] == want.hex() and res["msm"] == want.hex()

@@ -197,3 +197,57 @@ def test_gt_exp_bilinearity(m):
         assert lhs.Bytes() == rhs.Bytes()
         # Zr.Bytes() reduces (GroupOrder -> 0), so the exponent r itself goes through the batch call as raw bytes
         assert c.GtExpBatch(c.GenGt.Bytes(), c.order.to_bytes(32, "big"), 1) == c._gt_one
+
+
+# ---- (de)serialisation and validation on the device --------------------------------------------------
+@pytest.mark.parametrize("cid", CURVE_IDS)
+def test_point_codec_batches(m, cid):
+    """G1/G2 Compressed(), NewG*FromCompressed and the NewG*FromBytes checks for whole batches, against oracle/codec.py
+    (formats of SURVEY A.3; kilic == gnark byte equality is what reference math_test.go:879-945 pins)."""
+    import random
+    from oracle import codec
+    from oracle.pairing import Pairing
+    from oracle.params import CURVE_IDS as ORACLE_IDS
+    c = m.Curves[cid]
+    P, _ = ORACLE_IDS[cid]
+    C = Pairing(P).C
+    rnd = random.Random(900 + cid)
+    g1 = [None, C.g1, C.g1_neg(C.g1)] + [C.g1_mul(C.g1, rnd.randrange(1, P.r)) for _ in range(29)]
+    g2 = [None, C.g2, C.g2_neg(C.g2)] + [C.g2_mul(C.g2, rnd.randrange(1, P.r)) for _ in range(13)]
+    for g2flag, pts, to_b, to_c in ((0, g1, codec.g1_to_bytes, codec.g1_to_compressed),
+                                    (1, g2, codec.g2_to_bytes, codec.g2_to_compressed)):
+        n = len(pts)
+        unc = b"".join(to_b(P, p) for p in pts)
+        cmp_ = b"".join(to_c(P, p) for p in pts)
+        assert c.PointCodecBatch(g2flag, 1, unc, n) == cmp_
+        assert c.PointCodecBatch(g2flag, 0, cmp_, n) == unc
+        assert c.PointCodecBatch(g2flag, 2, unc, n) == b"\x01" * n
+    # single-element mirror methods
+    p = c.NewG1FromCompressed(codec.g1_to_compressed(P, g1[5]))
+    assert p.Bytes() == codec.g1_to_bytes(P, g1[5]) and p.Compressed() == codec.g1_to_compressed(P, g1[5])
+    q = c.NewG2FromCompressed(codec.g2_to_compressed(P, g2[5]))
+    assert q.Bytes() == codec.g2_to_bytes(P, g2[5]) and q.Compressed() == codec.g2_to_compressed(P, g2[5])
+    # rejects: an x with no point fails the call; a point off the curve / outside the subgroup gets verdict 0
+    x = 1
+    while pow((x ** 3 + P.b) % P.p, (P.p - 1) // 2, P.p) == 1:
+        x += 1
+    bad = bytearray(x.to_bytes(P.fp_bytes, "big"))
+    bad[0] |= 0x80
+    with pytest.raises(m.B200Error):
+        c.PointCodecBatch(0, 0, bytes(bad), 1)
+    off = bytearray(codec.g1_to_bytes(P, g1[4]))
+    off[-1] ^= 1
+    assert c.PointCodecBatch(0, 2, bytes(off) + codec.g1_to_bytes(P, g1[4]), 2) == b"\x00\x01"
+    if P.family != "bn":
+        # x = small value giving a curve point outside G1 (the cofactor is > 1): on-curve only passes, full check fails
+        xs = [v for v in range(1, 40) if pow((v ** 3 + P.b) % P.p, (P.p - 1) // 2, P.p) == 1]
+        cb = bytearray(xs[0].to_bytes(P.fp_bytes, "big"))
+        cb[0] |= 0x80
+        ub = c.PointCodecBatch(0, 0, bytes(cb), 1, m.NO_SUBGROUP_CHECK)
+        pt = codec.g1_from_bytes(P, ub)
+        assert C.g1_on_curve(pt)
+        if C.g1_add(C.g1_mul(pt, P.r - 1), pt) is not None:
+            assert c.PointCodecBatch(0, 2, ub, 1) == b"\x00"
+            assert c.PointCodecBatch(0, 2, ub, 1, m.NO_SUBGROUP_CHECK) == b"\x01"
+            with pytest.raises(m.B200Error):
+                c.PointCodecBatch(0, 0, bytes(cb), 1)

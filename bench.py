@@ -483,6 +483,35 @@ def run_extra(m, lib, dev, stream, torch):
         raise RuntimeError("BBS-style verification verdicts are wrong")
     out["config4_bls12_381_bbs_verify_12500_per_gpu_share"] = {"ms": ms, "verifications_per_s": n / ms * 1e3,
                                                                "what": "Mul2 -> Pairing2+FExp -> IsUnity, device resident"}
+    # the same verifications with the two fixed G2 arguments (public key, generator) as a resident line table (8f-1)
+    import ctypes
+    hl = ctypes.c_uint64()
+    m.check(lib.b200_g2_lines_upload(6, 2, m.buf_ptr(bytes.fromhex(pk["g2"]) + c.GenG2.Bytes()), 0, ctypes.byref(hl)))
+
+    def verify_fixed():
+        m.check(lib.b200_g1_mul2_batch(6, n, gen.data_ptr(), d_e.data_ptr(), d_A.data_ptr(), d_f.data_ptr(),
+                                       d_B.data_ptr(), m.DEVICE_PTRS))
+        m.check(lib.b200_pairing2_fixed_batch(hl.value, n, d_A.data_ptr(), None, d_B.data_ptr(), None, d_v.data_ptr(),
+                                              m.DEVICE_PTRS | m.FEXP | m.OUT_UNITY_ONLY))
+    d_v.zero_()
+    ms = timed(verify_fixed)
+    if not (d_v.cpu().numpy() == v).all():
+        raise RuntimeError("fixed-Q verification verdicts differ")
+    out["config4_bls12_381_bbs_verify_12500_fixed_q_tables"] = {"ms": ms, "verifications_per_s": n / ms * 1e3}
+    # fixed-Q Pairing2+FExp at the headline batch size (65,536 checks, same two G2 rows for every check)
+    n2 = 65536
+    gen2 = dev_bytes(c.GenG1.Bytes() * n2)
+    kk = rng.integers(0, 256, size=(n2, 32), dtype=np.uint8)
+    kk[:, 0] &= 0x3F
+    d_kk = torch.from_numpy(kk.reshape(-1)).to(dev)
+    d_P = torch.empty(n2 * c.G1ByteSize, dtype=torch.uint8, device=dev)
+    m.check(lib.b200_g1_mul_batch(6, n2, gen2.data_ptr(), d_kk.data_ptr(), d_P.data_ptr(), m.DEVICE_PTRS))
+    d_o = torch.empty(n2 * c.GtByteSize, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: m.check(lib.b200_pairing2_fixed_batch(hl.value, n2, d_P.data_ptr(), None, d_P.data_ptr(), None,
+                                                             d_o.data_ptr(), m.DEVICE_PTRS | m.FEXP)), reps=2)
+    out["next_pairing2_fexp_fixed_q_bls12_381_65536"] = {"ms": ms, "pairings_per_s": 2 * n2 / ms * 1e3}
+    m.check(lib.b200_g2_lines_free(hl.value))
+    del gen2, d_kk, d_P, d_o
     # SURVEY 8(f) row 3, the callers next to the hot path: Gt.Exp and G2.Mul batches on BLS12-381 (device resident)
     c = m.Curves[5]
     n = 16384

@@ -125,6 +125,17 @@ int b200_gt_mul_batch(int curve, size_t n, const void* gt_a, const void* gt_b, v
 int b200_gt_inv_batch(int curve, size_t n, const void* gt_a, void* gt_out, uint32_t flags);
 int b200_gt_exp_batch(int curve, size_t n, const void* gt_a, const void* scalars_be32, void* gt_out, uint32_t flags);
 
+/* ---- fixed-Q pairings: the BLS / BBS verification pattern, where the G2 arguments are a small set of
+   public keys and the generator (reference perf_test.go:248-259).  The G2 side of the Miller loop is computed once per
+   point into a resident line table; pairings against table rows then do no G2 arithmetic.  Results are bit-identical to
+   b200_pairing_batch / b200_pairing2_batch on the same points (same driver semantics per curve id, same flags).
+   q_idx / qa_idx / qb_idx: one uint32 row index per item; NULL = row 0 (pair a) and row 1 (pair b) for every item. */
+int b200_g2_lines_upload(int curve, size_t n_q, const void* g2_pts, uint32_t flags, uint64_t* handle);
+int b200_g2_lines_free(uint64_t handle);
+int b200_pairing_fixed_batch(uint64_t lines, size_t n, const void* g1, const uint32_t* q_idx, void* gt_out, uint32_t flags);
+int b200_pairing2_fixed_batch(uint64_t lines, size_t n, const void* g1a, const uint32_t* qa_idx, const void* g1b,
+                              const uint32_t* qb_idx, void* gt_out, uint32_t flags);
+
 /* ---- point (de)serialisation and validation for whole batches ----
    NewG1FromCompressed / NewG2FromCompressed (reference driver/gurvy/bn254.go:359-377, bls12381/bls12-381.go:551-569,
    kilic/bls12-381.go:370-394): compressed -> uncompressed Bytes() (or MONT limbs with B200_OUT_MONT).  A coordinate >= p,

@@ -52,6 +52,10 @@ PROTOTYPES = {
     "b200_g2_compress_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
     "b200_g1_validate_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
     "b200_g2_validate_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g2_lines_upload": (_int, [_int, _sz, _vp, _u32, ctypes.POINTER(_u64)]),
+    "b200_g2_lines_free": (_int, [_u64]),
+    "b200_pairing_fixed_batch": (_int, [_u64, _sz, _vp, _vp, _vp, _u32]),
+    "b200_pairing2_fixed_batch": (_int, [_u64, _sz, _vp, _vp, _vp, _vp, _vp, _u32]),
     "b200_launch_count": (_u64, []),
 }
 

@@ -204,6 +204,10 @@ MsmPlan resident_plan(const CurveVTable* vt, const Bases* bs, size_t n) {
     return pl;
 }
 std::map<uint64_t, Bases> g_bases;
+struct Lines {                          // fixed-Q line tables
+    int curve; int dev; size_t n_q; uint32_t* lines; uint8_t* qinf;
+};
+std::map<uint64_t, Lines> g_lines;
 uint64_t g_next_handle = 1;
 
 // carve the MSM workspace; returns bytes needed (buf may be null to size only)
@@ -303,6 +307,8 @@ void b200_shutdown(void) {
     g_free_ws.clear();
     for (auto& kv : g_bases) { cudaSetDevice(kv.second.dev); cudaFree(kv.second.pts); }
     g_bases.clear();
+    for (auto& kv : g_lines) { cudaSetDevice(kv.second.dev); cudaFree(kv.second.lines); cudaFree(kv.second.qinf); }
+    g_lines.clear();
     g_inited = false;
 }
 
@@ -617,6 +623,112 @@ int b200_g2_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags)
     CU(cudaStreamSynchronize(w.stream));
     if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
     return 0;
+}
+
+int b200_g2_lines_upload(int curve, size_t n_q, const void* g2_pts, uint32_t flags, uint64_t* handle) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!handle || !n_q || !g2_pts) return fail(B200_ERR_ARG, "null buffer");
+    const CurveVTable* vt = ci.vt;
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    const size_t g2sz = 4 * (size_t)vt->fp_bytes, row = vt->lines_row_words() * sizeof(uint32_t);
+    uint32_t* d_lines = nullptr;
+    uint8_t* d_inf = nullptr;
+    CU(cudaMalloc(&d_lines, n_q * row));
+    if (cudaMalloc(&d_inf, n_q) != cudaSuccess) { cudaFree(d_lines); return fail(B200_ERR_CUDA, "cudaMalloc"); }
+    int h_err = 0;
+    auto cleanup = [&]() { cudaFree(d_lines); cudaFree(d_inf); };
+    if (flags & B200_DEVICE_PTRS) {
+        int* d_err = device_err_flag(dev);
+        cudaMemsetAsync(d_err, 0, sizeof(int), t_stream);
+        cudaError_t e = vt->lines_build(n_q, (const uint8_t*)g2_pts, d_lines, d_inf, kernel_flags(flags), d_err, t_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, t_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(t_stream);
+        if (e != cudaSuccess) { cleanup(); return fail(B200_ERR_CUDA, "line table: %s", cudaGetErrorString(e)); }
+    } else {
+        WsGuard g(dev);
+        if (!g.w) { cleanup(); return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev); }
+        Workspace& w = *g.w;
+        if (int rc = w.reserve(n_q * g2sz)) { cleanup(); return rc; }
+        cudaError_t e = cudaMemcpyAsync(w.buf, g2_pts, n_q * g2sz, cudaMemcpyHostToDevice, w.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream);
+        if (e == cudaSuccess) e = vt->lines_build(n_q, w.buf, d_lines, d_inf, kernel_flags(flags), w.d_err, w.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+        if (e != cudaSuccess) { cleanup(); return fail(B200_ERR_CUDA, "line table: %s", cudaGetErrorString(e)); }
+    }
+    if (h_err) { cleanup(); return fail(B200_ERR_ENCODING, "input is not a canonical element encoding"); }
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint64_t h = g_next_handle++;
+    g_lines[h] = {curve, dev, n_q, d_lines, d_inf};
+    *handle = h;
+    return 0;
+}
+
+int b200_g2_lines_free(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_lines.find(handle);
+    if (it == g_lines.end()) return fail(B200_ERR_ARG, "unknown line-table handle %llu", (unsigned long long)handle);
+    cudaSetDevice(it->second.dev);
+    cudaFree(it->second.lines);
+    cudaFree(it->second.qinf);
+    g_lines.erase(it);
+    return 0;
+}
+
+static int pairing_fixed_common(uint64_t handle, int np, size_t n, const void* g1a, const uint32_t* qa, const void* g1b,
+                                const uint32_t* qb, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    Lines ln;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_lines.find(handle);
+        if (it == g_lines.end()) return fail(B200_ERR_ARG, "unknown line-table handle %llu", (unsigned long long)handle);
+        ln = it->second;
+    }
+    if (n == 0) return 0;
+    if (!g1a || !out || (np == 2 && !g1b)) return fail(B200_ERR_ARG, "null buffer");
+    if (ln.n_q < (size_t)np && (!qa || (np == 2 && !qb))) return fail(B200_ERR_ARG, "default rows need %d table entries", np);
+    CurveInfo ci;
+    curve_info(ln.curve, &ci);
+    const CurveVTable* vt = ci.vt;
+    uint32_t kf = kernel_flags(flags);
+    if (ci.kilic) kf |= B200_FEXP;
+    const size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    const size_t osz = (flags & B200_OUT_UNITY_ONLY) ? 1 : 12 * (size_t)vt->fp_bytes;
+    CU(cudaSetDevice(ln.dev));
+    if (flags & B200_DEVICE_PTRS) {
+        CU(vt->pairing_fixed(np, n, (const uint8_t*)g1a, qa, (const uint8_t*)g1b, qb, ln.lines, ln.qinf, (uint8_t*)out, kf,
+                             device_err_flag(ln.dev), t_stream));
+        return 0;
+    }
+    // row indices arrive from the host: reject out-of-range rows before they become device addresses
+    for (size_t i = 0; i < n; i++)
+        if ((qa && qa[i] >= ln.n_q) || (np == 2 && qb && qb[i] >= ln.n_q)) return fail(B200_ERR_ARG, "row index out of range");
+    std::vector<Piece> ins = {{g1a, g1sz, nullptr}};
+    if (np == 2) ins.push_back({g1b, g1sz, nullptr});
+    const int ia = qa ? (int)ins.size() : -1;
+    if (qa) ins.push_back({qa, 4, nullptr});
+    const int ib = (np == 2 && qb) ? (int)ins.size() : -1;
+    if (np == 2 && qb) ins.push_back({qb, 4, nullptr});
+    return staged_call(ln.dev, 0, n, ins, out, osz,
+                       [&](size_t m, std::vector<Piece>& p, uint8_t* d_out, int* d_err, cudaStream_t s) {
+                           return vt->pairing_fixed(np, m, p[0].dev, ia >= 0 ? (const uint32_t*)p[ia].dev : nullptr,
+                                                    np == 2 ? p[1].dev : nullptr,
+                                                    ib >= 0 ? (const uint32_t*)p[ib].dev : nullptr, ln.lines, ln.qinf,
+                                                    d_out, kf, d_err, s);
+                       });
+}
+
+int b200_pairing_fixed_batch(uint64_t lines, size_t n, const void* g1, const uint32_t* q_idx, void* gt_out, uint32_t flags) {
+    return pairing_fixed_common(lines, 1, n, g1, q_idx, nullptr, nullptr, gt_out, flags);
+}
+
+int b200_pairing2_fixed_batch(uint64_t lines, size_t n, const void* g1a, const uint32_t* qa_idx, const void* g1b,
+                              const uint32_t* qb_idx, void* gt_out, uint32_t flags) {
+    return pairing_fixed_common(lines, 2, n, g1a, qa_idx, g1b, qb_idx, gt_out, flags);
 }
 
 // op 0 decompress, 1 compress, 2 validate (launch.cuh: point_codec)

@@ -50,6 +50,13 @@ struct CurveVTable {
     cudaError_t (*g2_sum)(size_t n, const uint8_t* pts, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
     cudaError_t (*gt_op)(int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t flags, int* err,
                          cudaStream_t s);
+    // fixed-Q line tables -- rows of lines_row_words words per G2 point; pairings against table rows
+    size_t (*lines_row_words)();
+    cudaError_t (*lines_build)(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, uint32_t flags, int* err,
+                               cudaStream_t s);
+    cudaError_t (*pairing_fixed)(int np, size_t n, const uint8_t* g1a, const uint32_t* qa_idx, const uint8_t* g1b,
+                                 const uint32_t* qb_idx, const uint32_t* lines, const uint8_t* qinf, uint8_t* out,
+                                 uint32_t flags, int* err, cudaStream_t s);
     // point decompression (op 0) / compression (1) / validation (2) batches, g2 = 0 / 1
     cudaError_t (*point_codec)(int g2, int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err,
                                cudaStream_t s);
@@ -151,6 +158,11 @@ struct Launch {
                 if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_lines_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 1, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 2, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 1, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 2, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WB>, at, sb)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
                 it = tables.emplace(dev, std::make_pair((const uint32_t*)w, (const VmDirEntry*)d)).first;
@@ -198,6 +210,46 @@ struct Launch {
             vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n, in, out, flags, err,
                                                                                                     d_words, d_dir);
         }
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static size_t lines_row_words() { return (size_t)VmDriver<C>::nlines() * 3 * 2 * C::N; }
+    static cudaError_t lines_build(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, uint32_t flags, int* err,
+                                   cudaStream_t s) {
+        if (n_q == 0) return cudaSuccess;
+        const uint32_t* d_words = nullptr;
+        const VmDirEntry* d_dir = nullptr;
+        cudaError_t e = vm_setup(&d_words, &d_dir);
+        if (e != cudaSuccess) return e;
+        constexpr int W = B200_VM_WARPS_SMALL;
+        const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+        vm_lines_kernel<C, W><<<(unsigned)((n_q + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n_q, g2, lines, qinf, flags,
+                                                                                                   err, d_words, d_dir);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    template <int W>
+    static void fixed_launch(int np, size_t n, const uint8_t* g1a, const uint32_t* qa, const uint8_t* g1b, const uint32_t* qb,
+                             const uint32_t* lines, const uint8_t* qinf, uint8_t* out, uint32_t flags, int* err,
+                             const uint32_t* d_words, const VmDirEntry* d_dir, cudaStream_t s) {
+        const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
+        const unsigned nb = (unsigned)((n + gpb - 1) / gpb);
+        const size_t smem = vm_smem_bytes<C, W>();
+        if (np == 1)
+            vm_pairing_fixed_kernel<C, 1, W><<<nb, W * 32, smem, s>>>(n, g1a, qa, g1a, qa, lines, qinf, out, flags, err, d_words, d_dir);
+        else
+            vm_pairing_fixed_kernel<C, 2, W><<<nb, W * 32, smem, s>>>(n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir);
+    }
+    static cudaError_t pairing_fixed(int np, size_t n, const uint8_t* g1a, const uint32_t* qa, const uint8_t* g1b,
+                                     const uint32_t* qb, const uint32_t* lines, const uint8_t* qinf, uint8_t* out,
+                                     uint32_t flags, int* err, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        const uint32_t* d_words = nullptr;
+        const VmDirEntry* d_dir = nullptr;
+        cudaError_t e = vm_setup(&d_words, &d_dir);
+        if (e != cudaSuccess) return e;
+        if (small_batch(n)) fixed_launch<B200_VM_WARPS_SMALL>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
+        else fixed_launch<vm_warps<C>()>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
@@ -318,7 +370,7 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
-                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &point_codec, &msm_points, &msm_tables, &msm};
+                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec, &msm_points, &msm_tables, &msm};
         return &t;
     }
 };

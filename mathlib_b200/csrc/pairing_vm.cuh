@@ -21,6 +21,8 @@ template <class C> struct VmTables;
         static constexpr int QSTRIDE = VM_##NAME##_QSTRIDE;                                               \
         static constexpr int QBASE = VM_##NAME##_QBASE;                                                   \
         static constexpr int PBASE = VM_##NAME##_PBASE;                                                   \
+        static constexpr int TBASE = VM_##NAME##_TBASE;                                                   \
+        static constexpr int LINEOUT = VM_##NAME##_LINEOUT;                                               \
         static const uint32_t* host_words() { return H_VMW_##NAME; }                                      \
         static const VmDirEntry* host_dir() { return H_VMD_##NAME; }                                      \
     };
@@ -108,6 +110,107 @@ struct VmDriver {
             uint32_t t = cur; cur = nxt; nxt = t;
         }
         return cur;
+    }
+
+    // ---- fixed-Q Miller loop: the G2 side of every step comes from a precomputed line table -- per step
+    // three P-independent Fp2 coefficients per pair, copied into the pair's T slots -- and the SQRLINE / LINE programs
+    // evaluate them at P and fold them into f.  Same f as miller<NP>() (vm/driver_ref.py: miller_fixed).
+    // rowK: table row of pair K (nlines * 3 slots); lane `role` copies coefficient role % 3 of pair role / 3.
+    template <int NP>
+    B200_HD void load_lines(const uint32_t* row0, const uint32_t* row1, int step) {
+#if defined(__CUDA_ARCH__)
+        if (role >= 0 && role < 3 * NP) {
+            const int k = role / 3, j = role % 3;
+            const uint4* src = reinterpret_cast<const uint4*>((k ? row1 : row0) + ((size_t)step * 3 + j) * SW);
+            uint4* dst = reinterpret_cast<uint4*>(ctx.slots + (TB::TBASE + 3 * k + j) * SW);
+#pragma unroll
+            for (int i = 0; i < SW / 4; i++) dst[i] = src[i];
+        }
+        __syncwarp();
+#else
+        for (int r = 0; r < 3 * NP; r++) {
+            const int k = r / 3, j = r % 3;
+            const uint32_t* src = (k ? row1 : row0) + ((size_t)step * 3 + j) * SW;
+            uint32_t* dst = ctx.slots + (TB::TBASE + 3 * k + j) * SW;
+            for (int i = 0; i < SW; i++) dst[i] = src[i];
+        }
+#endif
+    }
+    template <int NP>
+    B200_HD uint32_t miller_fixed(const uint32_t* row0, const uint32_t* row1) {
+        uint32_t cur = 0, nxt = 6;
+        run(NP == 1 ? VP_INIT1 : VP_INIT2, cur, nxt, 0);
+        const bool sq_swaps = ((1 + NP) & 1) != 0, ln_swaps = (NP & 1) != 0;
+        const int len = PairingOps<C>::loop_len();
+        int top = len - 1;
+        while (PairingOps<C>::loop_digit(top) == 0) top--;
+        int step = 0;
+        for (int i = top - 1; i >= 0; i--) {
+            load_lines<NP>(row0, row1, step++);
+            run(NP == 1 ? VP_SQRLINE1 : VP_SQRLINE2, cur, nxt, 0);
+            if (sq_swaps) { uint32_t t = cur; cur = nxt; nxt = t; }
+            if (PairingOps<C>::loop_digit(i)) {
+                load_lines<NP>(row0, row1, step++);
+                run(NP == 1 ? VP_LINE1 : VP_LINE2, cur, nxt, 0);
+                if (ln_swaps) { uint32_t t = cur; cur = nxt; nxt = t; }
+            }
+        }
+        if (C::FAMILY == FAMILY_BN)
+            for (int t2 = 0; t2 < 2; t2++) {
+                load_lines<NP>(row0, row1, step++);
+                run(NP == 1 ? VP_LINE1 : VP_LINE2, cur, nxt, 0);
+                if (ln_swaps) { uint32_t t = cur; cur = nxt; nxt = t; }
+            }
+        if (C::X_NEG) {
+            run(VP_CONJ, nxt, cur, 0);
+            uint32_t t = cur; cur = nxt; nxt = t;
+        }
+        return cur;
+    }
+    // number of line evaluations of one Miller loop = rows of 3 slots per table entry
+    static B200_HD int nlines() {
+        const int len = PairingOps<C>::loop_len();
+        int top = len - 1;
+        while (PairingOps<C>::loop_digit(top) == 0) top--;
+        int n = 0;
+        for (int i = top - 1; i >= 0; i--) n += 1 + (PairingOps<C>::loop_digit(i) ? 1 : 0);
+        return n + (C::FAMILY == FAMILY_BN ? 2 : 0);
+    }
+    // table of one Q: runs the G2 side of the loop on pair 0 and writes (r0, r1, r2) of every step to `row`
+    B200_HD void precompute_lines(uint32_t* row) {
+        run(VP_INIT1, 0, 6, 0);
+        const int len = PairingOps<C>::loop_len();
+        int top = len - 1;
+        while (PairingOps<C>::loop_digit(top) == 0) top--;
+        int step = 0;
+        for (int i = top - 1; i >= 0; i--) {
+            run(VP_PRE_DBL, 0, 0, 0);
+            store_line(row, step++);
+            const int d = PairingOps<C>::loop_digit(i);
+            if (d) {
+                run(VP_PRE_ADD, 0, 0, d > 0 ? 0u : 1u);
+                store_line(row, step++);
+            }
+        }
+        if (C::FAMILY == FAMILY_BN) {
+            run(VP_PRE_TAIL1, 0, 0, 0);
+            store_line(row, step++);
+            run(VP_PRE_TAIL2, 0, 0, 0);
+            store_line(row, step++);
+        }
+    }
+    B200_HD void store_line(uint32_t* row, int step) {
+#if defined(__CUDA_ARCH__)
+        if (role >= 0 && role < 3) {
+            const uint32_t* src = ctx.slots + (TB::LINEOUT + role) * SW;
+            uint32_t* dst = row + ((size_t)step * 3 + role) * SW;
+            for (int i = 0; i < SW; i++) dst[i] = src[i];
+        }
+        __syncwarp();
+#else
+        for (int r = 0; r < 3; r++)
+            for (int i = 0; i < SW; i++) row[((size_t)step * 3 + r) * SW + i] = ctx.slots[(TB::LINEOUT + r) * SW + i];
+#endif
     }
 
     // ---- final exponentiation over NREGS Fp12 registers; returns the slot base of the result
@@ -424,6 +527,117 @@ vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* e
         const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
         const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+        if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
+    } else if (active) {
+        D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+    }
+}
+
+// ---- fixed-Q pairings --------------------------------------------------------------------------------
+// line tables of n_q G2 points: lines[q] = nlines * 3 slots (Montgomery), qinf[q] = 1 for the point at infinity
+template <class C, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)
+vm_lines_kernel(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, uint32_t flags, int* err,
+                const uint32_t* mc_words, const VmDirEntry* mc_dir) {
+    extern __shared__ uint32_t smem[];
+    constexpr int N = C::N;
+    constexpr int GPB = WARPS * B200_VM_GROUPS_PER_WARP;
+    uint32_t* s_slots = smem;
+    uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
+    uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
+    if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = lane / VM_G;
+    const int role = gw < B200_VM_GROUPS_PER_WARP ? lane % VM_G : -1;
+    const int gblock = warp * B200_VM_GROUPS_PER_WARP + (gw < B200_VM_GROUPS_PER_WARP ? gw : 0);
+    const size_t item = (size_t)blockIdx.x * GPB + gblock;
+    const bool active = role >= 0 && item < n_q;
+    VmDriver<C> D;
+    D.ctx.slots = s_slots + (size_t)gblock * vm_group_stride<C>();
+    D.ctx.kbank = s_kbank;
+    D.ctx.live = 3;
+    D.words = s_words;
+    D.dir = s_dir;
+    D.role = active ? role : -1;
+    typedef Codec<C> CD;
+    int e = 0, z = 0;
+    if (active) {
+        if (role >= 2) z = D.load_coord(role, 0, nullptr, g2 + item * CD::g2_size(), flags & FLAG_IN_MONT, &e);
+        else {
+            uint32_t* dst = D.ctx.slots + (VmTables<C>::PBASE) * 2 * N + role * N;
+            for (int i = 0; i < N; i++) dst[i] = 0;
+        }
+    }
+    const unsigned bz = __ballot_sync(0xffffffffu, z != 0);
+    if (__ballot_sync(0xffffffffu, e != 0)) {
+        if (lane == 0) atomicExch(err, 1);
+        return;
+    }
+    const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+    if (active && role == 0) qinf[item] = (((bz >> sh) & 60u) == 60u) ? 1 : 0;
+    __syncwarp();
+    D.precompute_lines(lines + (active ? item : 0) * (size_t)VmDriver<C>::nlines() * 3 * 2 * N);
+}
+
+// Pairing / Pairing2 with every G2 argument taken from a line table: check i uses rows qa_idx[i] (and qb_idx[i]); a null
+// index array means row 0 (pair a) / row 1 (pair b) for every check -- the BLS / BBS verification pattern.
+template <class C, int NP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)
+vm_pairing_fixed_kernel(size_t n, const uint8_t* g1a, const uint32_t* qa_idx, const uint8_t* g1b, const uint32_t* qb_idx,
+                        const uint32_t* lines, const uint8_t* qinf, uint8_t* out, uint32_t flags, int* err,
+                        const uint32_t* mc_words, const VmDirEntry* mc_dir) {
+    extern __shared__ uint32_t smem[];
+    constexpr int N = C::N;
+    constexpr int GPB = WARPS * B200_VM_GROUPS_PER_WARP;
+    uint32_t* s_slots = smem;
+    uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
+    uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
+    if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = lane / VM_G;
+    const int role = gw < B200_VM_GROUPS_PER_WARP ? lane % VM_G : -1;
+    const int gblock = warp * B200_VM_GROUPS_PER_WARP + (gw < B200_VM_GROUPS_PER_WARP ? gw : 0);
+    const size_t item = (size_t)blockIdx.x * GPB + gblock;
+    const bool active = role >= 0 && item < n;
+    VmDriver<C> D;
+    D.ctx.slots = s_slots + (size_t)gblock * vm_group_stride<C>();
+    D.ctx.kbank = s_kbank;
+    D.words = s_words;
+    D.dir = s_dir;
+    D.role = active ? role : -1;
+    typedef Codec<C> CD;
+    const bool in_mont = flags & FLAG_IN_MONT;
+    int e = 0, z0 = 0, z1 = 0;
+    if (active && role < 2) {
+        z0 = D.load_coord(role, 0, g1a + item * CD::g1_size(), nullptr, in_mont, &e);
+        if (NP == 2) z1 = D.load_coord(role, 1, g1b + item * CD::g1_size(), nullptr, in_mont, &e);
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, z0 != 0), b1 = __ballot_sync(0xffffffffu, z1 != 0);
+    if (__ballot_sync(0xffffffffu, e != 0)) {
+        if (lane == 0) atomicExch(err, 1);
+        return;
+    }
+    const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+    const size_t it = active ? item : 0;
+    const uint32_t ra = qa_idx ? qa_idx[it] : 0u, rb = NP == 2 ? (qb_idx ? qb_idx[it] : 1u) : 0u;
+    const bool dead0 = (((b0 >> sh) & 3u) == 3u) || qinf[ra] != 0;
+    const bool dead1 = NP == 2 ? ((((b1 >> sh) & 3u) == 3u) || qinf[rb] != 0) : true;
+    D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
+    __syncwarp();
+    const size_t rowsz = (size_t)VmDriver<C>::nlines() * 3 * 2 * N;
+    uint32_t fb = D.template miller_fixed<NP>(lines + ra * rowsz, lines + rb * rowsz);
+    if (flags & FLAG_FEXP) fb = D.final_exp(fb);
+    if (flags & FLAG_UNITY) {
+        const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
         if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
     } else if (active) {
         D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);

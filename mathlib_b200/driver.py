@@ -364,6 +364,40 @@ class Curve:
         check(lib.b200_gt_inv_batch(self.id, n, buf_ptr(a), out, flags))
         return out.raw[:n * self.GtByteSize]
 
+    # ---- fixed-Q pairings against resident G2 line tables ----
+    def G2LinesUpload(self, g2_pts, n_q, flags=0):
+        lib = load()
+        h = ctypes.c_uint64()
+        check(lib.b200_g2_lines_upload(self.id, n_q, buf_ptr(g2_pts), flags, ctypes.byref(h)))
+        return h.value
+
+    def G2LinesFree(self, handle):
+        check(load().b200_g2_lines_free(handle))
+
+    @staticmethod
+    def _idx(rows):
+        if rows is None:
+            return None
+        import array
+        return array.array("I", rows).tobytes()
+
+    def PairingFixedBatch(self, handle, g1, rows, n, flags=0):
+        lib = load()
+        osz = n if flags & OUT_UNITY_ONLY else n * self.GtByteSize
+        out = ctypes.create_string_buffer(max(osz, 1))
+        r = self._idx(rows)
+        check(lib.b200_pairing_fixed_batch(handle, n, buf_ptr(g1), buf_ptr(r) if r else None, out, flags))
+        return out.raw[:osz]
+
+    def Pairing2FixedBatch(self, handle, g1a, rows_a, g1b, rows_b, n, flags=0):
+        lib = load()
+        osz = n if flags & OUT_UNITY_ONLY else n * self.GtByteSize
+        out = ctypes.create_string_buffer(max(osz, 1))
+        ra, rb = self._idx(rows_a), self._idx(rows_b)
+        check(lib.b200_pairing2_fixed_batch(handle, n, buf_ptr(g1a), buf_ptr(ra) if ra else None, buf_ptr(g1b),
+                                            buf_ptr(rb) if rb else None, out, flags))
+        return out.raw[:osz]
+
     def PointCodecBatch(self, g2, op, data, n, flags=0):
         """op 0: compressed -> Bytes(); 1: Bytes() -> compressed; 2: Bytes() -> verdict bytes."""
         lib = load()

@@ -70,6 +70,81 @@ def miller(ctx, pairs):
     return slots, cur
 
 
+def precompute_lines(ctx, Q):
+    """Line table of a fixed G2 point: one (r0, r1, r2) triple per Miller step, in loop order.
+    Same control flow as csrc/pairing_vm.cuh: vm_lines_kernel."""
+    slots = [(0, 0)] * ctx.nslots
+    slots[PR.Q_BASE], slots[PR.Q_BASE + 1] = Q[0], Q[1]
+    ctx.run('INIT1', slots, (0, 6, 0))
+    digits = loop_digits(ctx)
+    top = len(digits) - 1
+    while digits[top] == 0:
+        top -= 1
+    table = []
+
+    def emit():
+        table.append(tuple(slots[PR.LINE_OUT + j] for j in range(3)))
+    for i in range(top - 1, -1, -1):
+        ctx.run('PRE_DBL', slots)
+        emit()
+        d = digits[i]
+        if d:
+            ctx.run('PRE_ADD', slots, (0, 0, 0 if d > 0 else 1))
+            emit()
+    if ctx.cv.family == 'bn':
+        ctx.run('PRE_TAIL1', slots)
+        emit()
+        ctx.run('PRE_TAIL2', slots)
+        emit()
+    return table
+
+
+def miller_fixed(ctx, pairs):
+    """pairs: list of (P | None, line table | None).  Returns (slots, f_base): the same f as miller() on (P, Q)."""
+    np_ = len(pairs)
+    slots = [(0, 0)] * ctx.nslots
+    live = [True, True]
+    for k, (P, tab) in enumerate(pairs):
+        live[k] = P is not None and tab is not None
+        slots[ctx.pbase + k] = P or (0, 0)
+    cur, nxt = 0, 6
+    ctx.run('INIT%d' % np_, slots, (cur, nxt, 0), live)
+    digits = loop_digits(ctx)
+    top = len(digits) - 1
+    while digits[top] == 0:
+        top -= 1
+    step = 0
+
+    def load():
+        nonlocal step
+        for k, (P, tab) in enumerate(pairs):
+            for j in range(3):
+                slots[PR.T_BASE + 3 * k + j] = tab[step][j] if tab is not None else (0, 0)
+        step += 1
+    sq_swaps = (1 + np_) % 2 == 1
+    ln_swaps = np_ % 2 == 1
+    for i in range(top - 1, -1, -1):
+        load()
+        ctx.run('SQRLINE%d' % np_, slots, (cur, nxt, 0), live)
+        if sq_swaps:
+            cur, nxt = nxt, cur
+        if digits[i]:
+            load()
+            ctx.run('LINE%d' % np_, slots, (cur, nxt, 0), live)
+            if ln_swaps:
+                cur, nxt = nxt, cur
+    if ctx.cv.family == 'bn':
+        for _ in range(2):
+            load()
+            ctx.run('LINE%d' % np_, slots, (cur, nxt, 0), live)
+            if ln_swaps:
+                cur, nxt = nxt, cur
+    if ctx.x_neg:
+        ctx.run('CONJ', slots, (nxt, cur, 0), live)
+        cur, nxt = nxt, cur
+    return slots, cur
+
+
 class Regs:
     def __init__(self, n, used):
         self.free = [r for r in range(n) if r not in used]

@@ -231,7 +231,7 @@ def _line_and_sparse(cv, f_cur, lines_per_pair, f_slots_cycle):
     return outs, f_cur
 
 
-def _double_pair(cv, k):
+def _double_pair(cv, k, raw=False):
     X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
     P = ref(C_ABS, p_base() + k)
     XY = mul(X, Y, name='XY')
@@ -256,10 +256,13 @@ def _double_pair(cv, k):
     else:                    # (r0,r1,r2) = (-H, 3J, I): w^0 = r0 yP, w^1 = r1 xP, w^3 = r2
         line = {0: dot([((H, NEG), (P, REAL1))]), 1: dot([(J, (P, REAL0))], scale=3), 3: I}
     tout = [(X3, (C_ABS, T_BASE + 3 * k)), (Y3, (C_ABS, T_BASE + 3 * k + 1)), (Z3, (C_ABS, T_BASE + 3 * k + 2))]
+    if raw:          # the P-independent coefficients (r0, r1, r2) of the comments above, for the fixed-Q line tables
+        r = (I, lin([(J, 3)]), lin([(H, -1)])) if cv.twist == 'M' else (lin([(H, -1)]), lin([(J, 3)]), I)
+        return tout, r
     return tout, line
 
 
-def _add_pair(cv, k, qx, qy, update=True):
+def _add_pair(cv, k, qx, qy, update=True, raw=False):
     X, Y, Z = ref(C_ABS, T_BASE + 3 * k), ref(C_ABS, T_BASE + 3 * k + 1), ref(C_ABS, T_BASE + 3 * k + 2)
     P = ref(C_ABS, p_base() + k)
     O = dot([((qy, NEG), Z)], lin=[(Y, 1)], name='O')
@@ -278,6 +281,9 @@ def _add_pair(cv, k, qx, qy, update=True):
         Y3 = dot([(GmH, O), ((Y, NEG), E)])
         Z3 = mul(E, Z)
         tout = [(X3, (C_ABS, T_BASE + 3 * k)), (Y3, (C_ABS, T_BASE + 3 * k + 1)), (Z3, (C_ABS, T_BASE + 3 * k + 2))]
+    if raw:
+        r = (J, lin([(O, -1)]), lin([(L, 1)])) if cv.twist == 'M' else (lin([(L, 1)]), lin([(O, -1)]), J)
+        return tout, r
     if cv.twist == 'M':      # (J, -O, L)
         line = {0: J, 2: dot([((O, NEG), (P, REAL0))]), 3: dot([(L, (P, REAL1))])}
     else:                    # (L, -O, J)
@@ -362,6 +368,79 @@ def prog_bn_tail(cv, np_):
     return compile_program('BNTAIL%d' % np_, outs, miller_temps())
 
 
+# ------------------------------------------------------------------------------------------------ fixed-Q programs
+# when the G2 arguments are fixed (public keys, the generator) the G2 side of every Miller step is
+# computed once into a LINE TABLE: per step three P-independent Fp2 coefficients (r0, r1, r2).  At run time the driver
+# copies a step's coefficients of pair k into the pair's T slots and the programs below evaluate them at P and fold them
+# into f -- same values as the DBL / ADD / BNTAIL programs, without any G2 arithmetic.
+LINE_OUT = T_BASE + 3          # precompute programs work on pair 0 and leave (r0, r1, r2) in pair 1's T slots
+
+
+def _fixed_line(cv, k):
+    r0, r1, r2 = (ref(C_ABS, T_BASE + 3 * k + j) for j in range(3))
+    P = ref(C_ABS, p_base() + k)
+    if cv.twist == 'M':      # w^0 = r0, w^2 = r1 xP, w^3 = r2 yP
+        return {0: r0, 2: dot([(r1, (P, REAL0))]), 3: dot([(r2, (P, REAL1))])}
+    return {0: dot([(r0, (P, REAL1))]), 1: dot([(r1, (P, REAL0))]), 3: r2}
+
+
+def prog_fixed(cv, np_, square):
+    """f <- [f^2] * prod_k line_k(P_k)   (SQRLINE = the DBL programs' counterpart, LINE = ADD's / each BN tail line)"""
+    f = regs(C_B1)
+    outs = []
+    if square:
+        f_cur = f12_sqr_nodes(f)
+        set_group(f_cur, 1)
+        cyc = _f_cycle(1 + np_)
+        outs += bind(f_cur, cyc[0])
+        cyc = cyc[1:]
+    else:
+        f_cur = f
+        cyc = _f_cycle(np_)
+    lines = [_fixed_line(cv, k) for k in range(np_)]
+    for k in range(np_):
+        set_group([v for v in lines[k].values() if v.kind != 'ref'], 2)        # all P-scalings share one phase
+    for k in range(np_):
+        nodes = sparse_mul_nodes(f_cur, lines[k], cv.supp, pred=k + 1, alt=f_cur)
+        set_group(nodes, 3 + k)
+        outs += bind(nodes, cyc[k])
+        f_cur = nodes
+    return compile_program(('SQRLINE%d' if square else 'LINE%d') % np_, outs, miller_temps())
+
+
+def _bind_raw(r):
+    outs = []
+    for j, v in enumerate(r):
+        if v.out is not None or v.kind == 'ref':
+            v = lin([(v, 1)])
+        outs.append((v, (C_ABS, LINE_OUT + j)))
+    return outs
+
+
+def prog_pre_dbl(cv):
+    t, r = _double_pair(cv, 0, raw=True)
+    return compile_program('PRE_DBL', t + _bind_raw(r), miller_temps())
+
+
+def prog_pre_add(cv):
+    qx, qy = ref(C_ABS, Q_BASE), ref(C_B3, Q_BASE + 1)
+    t, r = _add_pair(cv, 0, qx, qy, raw=True)
+    return compile_program('PRE_ADD', t + _bind_raw(r), miller_temps())
+
+
+def prog_pre_tail(cv, second):
+    """BN254 tail: line through T and pi(Q) (with T += pi(Q)), then the line through the new T and -pi^2(Q)"""
+    qx, qy = ref(C_ABS, Q_BASE), ref(C_ABS, Q_BASE + 1)
+    if not second:
+        q1x = dot([((qx, CONJ), const(k_frob(1, 2)))])
+        q1y = dot([((qy, CONJ), const(k_frob(1, 3)))])
+        t, r = _add_pair(cv, 0, q1x, q1y, raw=True)
+        return compile_program('PRE_TAIL1', t + _bind_raw(r), miller_temps())
+    q2x = dot([(qx, const(k_frob(2, 2)))])
+    t, r = _add_pair(cv, 0, q2x, qy, update=False, raw=True)
+    return compile_program('PRE_TAIL2', _bind_raw(r), miller_temps())
+
+
 def prog_init(np_):
     """f = 1 (into B1), Z_k = 1, -y_k"""
     one, zero = const(K_ONE), const(K_ZERO)
@@ -396,4 +475,12 @@ def build_all(curve_name):
     progs['F12_SQR'] = prog_f12_sqr()
     progs['F12_MULP'] = prog_f12_mulp()
     progs['GT_ONE'] = prog_gt_one()
+    for np_ in (1, 2):
+        progs['SQRLINE%d' % np_] = prog_fixed(cv, np_, True)
+        progs['LINE%d' % np_] = prog_fixed(cv, np_, False)
+    progs['PRE_DBL'] = prog_pre_dbl(cv)
+    progs['PRE_ADD'] = prog_pre_add(cv)
+    if cv.family == 'bn':
+        progs['PRE_TAIL1'] = prog_pre_tail(cv, False)
+        progs['PRE_TAIL2'] = prog_pre_tail(cv, True)
     return progs

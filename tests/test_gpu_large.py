@@ -234,3 +234,50 @@ def test_multi_gpu_msm_matches_single(m):
     t.join()
     m.check(lib2.b200_set_device(0))
     assert res["multi"] == c.MsmBatch(pts, ks.tobytes(), n)
+
+
+@pytest.mark.parametrize("cid", [1, 3, 4, 5])
+def test_fixed_q_pairings_match_general_path(m, cid):
+    """pairings against resident G2 line tables give the same bytes as Pairing / Pairing2 on the same points
+    (raw Miller value, exponentiated value and unity verdict), with per-check row indices, the default rows, an infinity
+    row and infinity G1 arguments."""
+    import json
+    import os
+    c = m.Curves[cid]
+    n = 300
+    g1a, g2a, g1b, g2b, _ = rand_inputs(m, cid, n, seed=300 + cid)
+    gsz, qsz = c.G1ByteSize, c.G2ByteSize
+    # table: 6 distinct public keys out of the batch, the generator, and the point at infinity
+    inf2 = bytearray(qsz)
+    if c.fp_bytes == 48:
+        inf2[0] = 0x40
+    rows = [g2a[i * qsz:(i + 1) * qsz] for i in range(6)] + [c.GenG2.Bytes(), bytes(inf2)]
+    h = c.G2LinesUpload(b"".join(rows), len(rows))
+    rnd = random.Random(5 + cid)
+    ra = [rnd.randrange(len(rows)) for _ in range(n)]
+    rb = [rnd.randrange(len(rows)) for _ in range(n)]
+    g1a = c._g1_inf + g1a[gsz:]                                   # an infinity G1 in slot a of check 0
+    qa = b"".join(rows[r] for r in ra)
+    qb = b"".join(rows[r] for r in rb)
+    for flags in (0, m.FEXP, m.FEXP | m.OUT_UNITY_ONLY):
+        assert c.Pairing2FixedBatch(h, g1a, ra, g1b, rb, n, flags) == c.Pairing2Batch(g1a, qa, g1b, qb, n, flags)
+        assert c.PairingFixedBatch(h, g1b, rb, n, flags) == c.PairingBatch(g1b, qb, n, flags)
+    # default rows: (row 0, row 1) for every check -- the BLS verification shape e(A_i, pk) * e(B_i, g2)
+    want = c.Pairing2Batch(g1a, rows[0] * n, g1b, rows[1] * n, n, m.FEXP)
+    assert c.Pairing2FixedBatch(h, g1a, None, g1b, None, n, m.FEXP) == want
+    # valid BLS-style checks come out as unity: e(aG1, bG2) * e(-ab G1, G2) = 1 with pk = bG2 in row 0, G2 in row 1
+    with open(os.path.join(os.path.dirname(__file__), "golden", "g2_pool.json")) as f:
+        pk = json.load(f)[str({3: 3, 5: 3, 1: 1, 4: 4}[cid])][0]
+    h2 = c.G2LinesUpload(bytes.fromhex(pk["g2"]) + c.GenG2.Bytes(), 2)
+    b = int(pk["b"], 16)
+    a = [rnd.randrange(1, c.order) for _ in range(64)]
+    A = b"".join(p.Bytes() for p in c.G1MulBatch(c.GenG1.Bytes() * 64, b"".join(x.to_bytes(32, "big") for x in a), 64))
+    B = b"".join(p.Bytes() for p in c.G1MulBatch(
+        c.GenG1.Bytes() * 64, b"".join(((c.order - x * b) % c.order).to_bytes(32, "big") for x in a), 64))
+    assert c.Pairing2FixedBatch(h2, A, None, B, None, 64, m.FEXP | m.OUT_UNITY_ONLY) == b"\x01" * 64
+    with pytest.raises(m.B200Error):
+        c.Pairing2FixedBatch(h2, A, [0] * 64, B, [2] * 64, 64, m.FEXP)          # row index out of range
+    c.G2LinesFree(h)
+    c.G2LinesFree(h2)
+    with pytest.raises(m.B200Error):
+        c.Pairing2FixedBatch(h2, A, None, B, None, 64, m.FEXP)

@@ -52,6 +52,22 @@ def test_vm_gt_exp_matches_oracle(vmname):
         assert DR.f12_from_slots(slots, ob) == T.f12_pow(f, k)
 
 
+@pytest.mark.parametrize("vmname", ['BLS381', 'BN254', 'BLS377'])
+def test_vm_fixed_q_lines_match_miller(vmname):
+    """Fixed-Q line tables: PRE_* programs + SQRLINE / LINE reproduce the raw Miller value of the DBL / ADD
+    programs bit for bit, for one and two pairs and with a dead pair."""
+    ctx, pr = make_ctx(vmname)
+    C, P = pr.C, pr.P
+    rnd = random.Random(43)
+    Pa, Qa = C.g1_mul(C.g1, rnd.randrange(P.r)), C.g2_mul(C.g2, rnd.randrange(P.r))
+    Pb, Qb = C.g1_mul(C.g1, rnd.randrange(P.r)), C.g2_mul(C.g2, rnd.randrange(P.r))
+    ta, tb = DR.precompute_lines(ctx, Qa), DR.precompute_lines(ctx, Qb)
+    for pairs, fixed in (([(Pa, Qa)], [(Pa, ta)]), ([(Pa, Qa), (Pb, Qb)], [(Pa, ta), (Pb, tb)]),
+                         ([(None, Qa), (Pb, Qb)], [(None, ta), (Pb, tb)]), ([(Pa, Qa), (Pb, None)], [(Pa, ta), (Pb, None)])):
+        slots, fb = DR.miller_fixed(ctx, fixed)
+        assert DR.f12_from_slots(slots, fb) == pr.miller_projective(pairs)
+
+
 def test_program_budgets():
     from mathlib_b200.vm import programs as PR
     for name in PR.CURVES:

@@ -121,7 +121,7 @@ struct Launch {
                           cudaStream_t s) {
         const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
         const unsigned nb = (unsigned)((n + gpb - 1) / gpb);
-        const size_t smem = vm_smem_bytes<C, W>();
+        const size_t smem = vm_smem_bytes<C, W, true>();
         if (np == 1)
             vm_pairing_kernel<C, 1, W><<<nb, W * 32, smem, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err, d_words, d_dir);
         else
@@ -150,20 +150,22 @@ struct Launch {
                 if ((e = cudaMemcpy(d, VmTables<C>::host_dir(), sizeof(VmDirEntry) * VP_COUNT, cudaMemcpyHostToDevice)) !=
                     cudaSuccess) return e;
                 constexpr int WB = vm_warps<C>(), WS = B200_VM_WARPS_SMALL;
-                const int sb = (int)vm_smem_bytes<C, WB>(), ss = (int)vm_smem_bytes<C, WS>();
+                constexpr int WX = vm_warps_x<C>();
+                const int sb = (int)vm_smem_bytes<C, WX>(), ss = (int)vm_smem_bytes<C, WS>();
+                const int cb = (int)vm_smem_bytes<C, WB, true>(), cs = (int)vm_smem_bytes<C, WS, true>();
                 const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
-                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WB>, at, sb)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WB>, at, sb)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WB>, at, sb)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WS>, at, ss)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WS>, at, ss)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WB>, at, cb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WB>, at, cb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WB>, at, cb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WS>, at, cs)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WS>, at, cs)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WS>, at, cs)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_lines_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 1, WB>, at, sb)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 2, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 1, WX>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 2, WX>, at, sb)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 1, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 2, WS>, at, ss)) != cudaSuccess) return e;
-                if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WB>, at, sb)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WX>, at, sb)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_gt_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
                 it = tables.emplace(dev, std::make_pair((const uint32_t*)w, (const VmDirEntry*)d)).first;
             }
@@ -202,13 +204,13 @@ struct Launch {
         if (small_batch(n)) {
             constexpr int W = B200_VM_WARPS_SMALL;
             const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
-            vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n, in, out, flags, err,
-                                                                                                    d_words, d_dir);
+            vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W, true>(), s>>>(n, in, out, flags,
+                                                                                                          err, d_words, d_dir);
         } else {
             constexpr int W = vm_warps<C>();
             const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
-            vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(n, in, out, flags, err,
-                                                                                                    d_words, d_dir);
+            vm_fexp_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W, true>(), s>>>(n, in, out, flags,
+                                                                                                          err, d_words, d_dir);
         }
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
@@ -249,7 +251,7 @@ struct Launch {
         cudaError_t e = vm_setup(&d_words, &d_dir);
         if (e != cudaSuccess) return e;
         if (small_batch(n)) fixed_launch<B200_VM_WARPS_SMALL>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
-        else fixed_launch<vm_warps<C>()>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
+        else fixed_launch<vm_warps_x<C>()>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
@@ -266,7 +268,7 @@ struct Launch {
             vm_gt_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(op, n, a, b, out, flags,
                                                                                                   err, d_words, d_dir);
         } else {
-            constexpr int W = vm_warps<C>();
+            constexpr int W = vm_warps_x<C>();
             const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
             vm_gt_kernel<C, W><<<(unsigned)((n + gpb - 1) / gpb), W * 32, vm_smem_bytes<C, W>(), s>>>(op, n, a, b, out, flags,
                                                                                                   err, d_words, d_dir);

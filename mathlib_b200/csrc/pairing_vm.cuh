@@ -18,6 +18,7 @@ template <class C> struct VmTables;
         static constexpr int NSLOTS = VM_##NAME##_NSLOTS;                                                 \
         static constexpr int NREGS = VM_##NAME##_NREGS;                                                   \
         static constexpr int NWORDS = VM_##NAME##_NWORDS;                                                 \
+        static constexpr int NWORDS_CORE = VM_##NAME##_NWORDS_CORE;                                       \
         static constexpr int QSTRIDE = VM_##NAME##_QSTRIDE;                                               \
         static constexpr int QBASE = VM_##NAME##_QBASE;                                                   \
         static constexpr int PBASE = VM_##NAME##_PBASE;                                                   \
@@ -410,8 +411,13 @@ struct VmDriver {
 // ~200 registers, so 8 resident warps is the register-file limit (12 warps need <= 168 registers, which the slower
 // product-scanning variant reaches: measured 103.7 ms vs 99.9 ms per 65,536 checks for this shape).
 #define B200_VM_WARPS_MAX 4
-// BN254's microcode is larger (BN tail programs, 8-register final exponentiation): 10 warps keep it inside 227 KB
-template <class C> __host__ __device__ constexpr int vm_warps() { return C::N == 8 ? 10 : B200_VM_WARPS_MAX; }
+#ifndef B200_VM_WARPS_BN
+#define B200_VM_WARPS_BN 11
+#endif
+// BN254 (8-limb operands, ~160 registers): one block of 11 warps per SM for the Pairing / FExp kernels (55 slot files +
+// the core microcode = 220 KB); the kernels that stage the full microcode (fixed-Q, Gt ops) use 10
+template <class C> __host__ __device__ constexpr int vm_warps() { return C::N == 8 ? B200_VM_WARPS_BN : B200_VM_WARPS_MAX; }
+template <class C> __host__ __device__ constexpr int vm_warps_x() { return C::N == 8 ? 10 : B200_VM_WARPS_MAX; }
 #define B200_VM_GROUPS_PER_WARP 5
 #define B200_VM_GROUP_PAD 4          // words; staggers the groups across shared-memory banks
 
@@ -419,10 +425,15 @@ template <class C>
 __host__ __device__ constexpr size_t vm_group_stride() { return (size_t)VmTables<C>::NSLOTS * 2 * C::N + B200_VM_GROUP_PAD; }
 // small batches use 4-warp blocks (20 groups) so that they spread over more SMs
 #define B200_VM_WARPS_SMALL 4
-template <class C, int WARPS>
+// CORE = true: only the programs of the Pairing / FExp kernels are staged (the microcode words before F12_SQR); the
+// fixed-Q, Gt and line-table kernels stage everything.  Keeps the headline kernel's shared-memory footprint unchanged
+// by the neighbouring rows' programs.
+template <class C, bool CORE>
+__host__ __device__ constexpr int vm_nwords() { return CORE ? VmTables<C>::NWORDS_CORE : VmTables<C>::NWORDS; }
+template <class C, int WARPS, bool CORE = false>
 __host__ __device__ constexpr size_t vm_smem_bytes() {
     return 4 * ((size_t)WARPS * B200_VM_GROUPS_PER_WARP * vm_group_stride<C>() + (size_t)VM_KBANK * 2 * C::N +
-                (size_t)VmTables<C>::NWORDS + VP_COUNT * 2);
+                (size_t)vm_nwords<C, CORE>() + VP_COUNT * 2);
 }
 
 template <class C, int NP, int WARPS>
@@ -435,8 +446,8 @@ vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_
     uint32_t* s_slots = smem;
     uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
     uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
-    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
-    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS_CORE);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS_CORE; i += blockDim.x) s_words[i] = mc_words[i];
     if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
     if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
     __syncthreads();
@@ -495,8 +506,8 @@ vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* e
     uint32_t* s_slots = smem;
     uint32_t* s_kbank = s_slots + GPB * vm_group_stride<C>();
     uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
-    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS);
-    for (int i = threadIdx.x; i < VmTables<C>::NWORDS; i += blockDim.x) s_words[i] = mc_words[i];
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS_CORE);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS_CORE; i += blockDim.x) s_words[i] = mc_words[i];
     if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
     if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
     __syncthreads();

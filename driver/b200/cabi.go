@@ -148,3 +148,53 @@ func pointCodec(curve, g2, op, n int, in []byte, outElem int, flags uint32) []by
 	check("set bytes", rc)
 	return out
 }
+
+// ---- fixed-Q pairings against resident G2 line tables (SURVEY 8f-1) ----
+
+// LineTable is a resident table of Miller-loop line coefficients for a fixed set of G2 points (public keys, the
+// generator).  Free releases the device memory; a finalizer is not installed because the table is usually process-wide.
+type LineTable struct {
+	curve  int
+	handle C.uint64_t
+	gtSize int
+}
+
+// NewLineTable precomputes the G2 side of the Miller loop for the given points (reference Bytes() encoding, concatenated).
+func NewLineTable(c *Curve, g2Points []byte) *LineTable {
+	var h C.uint64_t
+	n := len(g2Points) / c.g2Size()
+	check("line table", C.b200_g2_lines_upload(C.int(c.id), C.size_t(n), ptr(g2Points), 0, &h))
+	return &LineTable{curve: c.id, handle: h, gtSize: c.gtSize()}
+}
+
+func (t *LineTable) Free() { check("line table free", C.b200_g2_lines_free(t.handle)) }
+
+func idxPtr(rows []uint32) *C.uint32_t {
+	if len(rows) == 0 {
+		return nil
+	}
+	return (*C.uint32_t)(unsafe.Pointer(&rows[0]))
+}
+
+// Pairing2Batch: n x e(rowA_i, p1a_i) * e(rowB_i, p1b_i); nil row slices mean row 0 / row 1 for every check.
+// With verdictOnly the result is one byte per check (Gt.IsUnity after FExp).
+func (t *LineTable) Pairing2Batch(n int, g1a []byte, rowsA []uint32, g1b []byte, rowsB []uint32, flags uint32) []byte {
+	size := t.gtSize
+	if flags&flagUnityOnly != 0 {
+		size = 1
+	}
+	out := make([]byte, n*size)
+	check("pairing 2", C.b200_pairing2_fixed_batch(t.handle, C.size_t(n), ptr(g1a), idxPtr(rowsA), ptr(g1b), idxPtr(rowsB),
+		ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+func (t *LineTable) PairingBatch(n int, g1 []byte, rows []uint32, flags uint32) []byte {
+	size := t.gtSize
+	if flags&flagUnityOnly != 0 {
+		size = 1
+	}
+	out := make([]byte, n*size)
+	check("pairing", C.b200_pairing_fixed_batch(t.handle, C.size_t(n), ptr(g1), idxPtr(rows), ptr(out), C.uint32_t(flags)))
+	return out
+}

@@ -314,23 +314,27 @@ struct VmDriver {
 
     // ---- Gt.Exp (reference driver/math.go:359; impls bn254.go:187-191, kilic/bls12-381.go:185-199): the Fp12 in
     // register 0 raised to a 256-bit exponent (32 bytes big-endian, used as given) by a left-to-right ladder of generic
-    // squarings and multiplies predicated on the group's exponent bit -- the groups of a warp run in lock-step, each on
-    // its own exponent.  `top` = number of ladder steps (warp-uniform, >= this exponent's bit length).  Same sequence as
-    // vm/driver_ref.py:gt_exp.  Returns the slot base of the result.
+    // squarings and multiplies predicated on the group's exponent digit -- the groups of a warp run in lock-step, each on
+    // its own exponent.  `top` = warp-uniform bit length (>= this exponent's).  Same sequence as vm/driver_ref.py:gt_exp.
+    // Returns the slot base of the result.
     B200_HD uint32_t gt_exp(const uint8_t* k_be32, int top) {
-        const uint32_t acc = 6, tmp = 12;
-        run(VP_GT_ONE, acc, 0, 0);
-        uint32_t kw = 0;
-        for (int i = top - 1; i >= 0; i--) {
-            if (i == top - 1 || (i & 31) == 31) {
-                const uint8_t* q = k_be32 + 28 - 4 * (i >> 5);
-                kw = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
-            }
-            run(VP_F12_SQR, tmp, acc, 0);
-            ctx.live = (kw >> (i & 31)) & 1u;
-            run(VP_F12_MULP, acc, tmp, 0);
+        // registers: a = 0, a^2 = 18, a^3 = 24; accumulator ping-pongs between 6 and 12.  2-bit windows: two squarings and
+        // one multiply by a^d per digit d, the table entry picked through the group's own B3 base (0 / 18 / 24), d = 0
+        // predicated off.
+        uint32_t cur = 6, oth = 12;
+        run(VP_F12_SQR, 18, 0, 0);
+        run(VP_F12_MUL, 24, 18, 0);
+        run(VP_GT_ONE, cur, 0, 0);
+        for (int j = (top + 1) / 2 - 1; j >= 0; j--) {
+            const int bit = 2 * j;
+            const uint32_t d = (k_be32[31 - (bit >> 3)] >> (bit & 7)) & 3u;
+            run(VP_F12_SQR, oth, cur, 0);
+            run(VP_F12_SQR, cur, oth, 0);
+            ctx.live = d != 0 ? 1u : 0u;
+            run(VP_F12_MULP, oth, cur, d == 2 ? 18u : (d == 3 ? 24u : 0u));
+            const uint32_t t = cur; cur = oth; oth = t;
         }
-        return acc;
+        return cur;
     }
     static B200_HD int scalar_bitlen(const uint8_t* k_be32) {
         for (int b = 0; b < 32; b++)

@@ -245,16 +245,23 @@ def final_exp(ctx, slots, f_base):
     return 6 * t0
 
 
-def gt_exp(ctx, slots, k):
-    """Gt.Exp: the Fp12 in register 0 (slots 0..5) raised to the integer k >= 0 by a left-to-right square-and-multiply
-    ladder; the multiply is predicated on the exponent bit (the kernel runs the groups of a warp in lock-step, each with
-    its own exponent).  Returns the slot base of the result."""
-    acc, tmp = 1, 2
-    ctx.run('GT_ONE', slots, (6 * acc, 0, 0))
-    for i in range(k.bit_length() - 1, -1, -1):
-        ctx.run('F12_SQR', slots, (6 * tmp, 6 * acc, 0))
-        ctx.run('F12_MULP', slots, (6 * acc, 6 * tmp, 0), (bool((k >> i) & 1), True))
-    return 6 * acc
+def gt_exp(ctx, slots, k, top=None):
+    """Gt.Exp: the Fp12 in register 0 (slots 0..5) raised to the integer k >= 0 by a left-to-right ladder over 2-bit
+    digits: two generic squarings and one multiply by a^d per digit, d = 0 predicated off (the kernel runs the groups of a
+    warp in lock-step, each with its own exponent, so the multiply is always executed).  `top` = bit length used by the
+    ladder (the kernel takes the warp maximum).  Returns the slot base of the result."""
+    cur, oth = 6, 12
+    ctx.run('F12_SQR', slots, (18, 0, 0))
+    ctx.run('F12_MUL', slots, (24, 18, 0))
+    ctx.run('GT_ONE', slots, (cur, 0, 0))
+    top = k.bit_length() if top is None else top
+    for j in range((top + 1) // 2 - 1, -1, -1):
+        d = (k >> (2 * j)) & 3
+        ctx.run('F12_SQR', slots, (oth, cur, 0))
+        ctx.run('F12_SQR', slots, (cur, oth, 0))
+        ctx.run('F12_MULP', slots, (oth, cur, {0: 0, 1: 0, 2: 18, 3: 24}[d]), (d != 0, True))
+        cur, oth = oth, cur
+    return cur
 
 
 def f12_from_slots(slots, base):

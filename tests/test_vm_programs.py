@@ -47,7 +47,7 @@ def test_vm_gt_exp_matches_oracle(vmname):
         g = [(rnd.randrange(P.p), rnd.randrange(P.p)) for _ in range(6)]
         slots = [(0, 0)] * ctx.nslots
         slots[0:6] = g
-        ob = DR.gt_exp(ctx, slots, k)
+        ob = DR.gt_exp(ctx, slots, k, top=k.bit_length() + rnd.randrange(0, 4))     # longer ladders (warp maximum) too
         f = ((g[0], g[2], g[4]), (g[1], g[3], g[5]))
         assert DR.f12_from_slots(slots, ob) == T.f12_pow(f, k)
 

@@ -236,14 +236,14 @@ def _double_pair(cv, k, raw=False):
     P = ref(C_ABS, p_base() + k)
     XY = mul(X, Y, name='XY')
     B = sqr(Y, name='B')
-    C = sqr(Z, name='C')
     H = dot([((Y, DBL), Z)], name='H')
     J = sqr(X, name='J')
+    # E = 3 b' Z^2 straight out of a multiplier op (scale applied after the reduction): no separate linear phase
     if cv.btw_is_4xi:
-        E = lin([((C, XI), 12)], name='E')
+        E = dot([((Z, XI | DBL), Z)], scale=6, name='E')            # b' = 4 xi: 3 b' Z^2 = 6 * (2 xi Z) * Z
     else:
-        Cb = mul(C, const(K_BTW), name='Cb')
-        E = lin([(Cb, 3)], name='E')
+        C = sqr(Z, name='C')
+        E = dot([(C, const(K_BTW))], scale=3, name='E')
     F3 = lin([(E, 3)], name='F3')
     Gv = lin([(B, 1), (E, 3)], halve=True, name='G')
     BmF = lin([(B, 1), (E, -3)], name='BmF')
@@ -276,7 +276,7 @@ def _add_pair(cv, k, qx, qy, update=True, raw=False):
         Fv = mul(Z, Cc)
         Gv = mul(X, D)
         H = lin([(E, 1), (Fv, 1), (Gv, -2)])
-        GmH = lin([(Gv, 1), (H, -1)])
+        GmH = lin([(Gv, 3), (E, -1), (Fv, -1)])          # = Gv - H, written on H's inputs: same phase as H
         X3 = mul(L, H)
         Y3 = dot([(GmH, O), ((Y, NEG), E)])
         Z3 = mul(E, Z)
@@ -351,7 +351,7 @@ def prog_bn_tail(cv, np_):
         Cc, D = sqr(O), sqr(L)
         E, Fv, Gv = mul(L, D), mul(Z, Cc), mul(X, D)
         H = lin([(E, 1), (Fv, 1), (Gv, -2)])
-        GmH = lin([(Gv, 1), (H, -1)])
+        GmH = lin([(Gv, 3), (E, -1), (Fv, -1)])          # = Gv - H, written on H's inputs: same phase as H
         X3, Y3, Z3 = mul(L, H), dot([(GmH, O), ((Y, NEG), E)]), mul(E, Z)
         line1 = {0: dot([(L, (P, REAL1))]), 1: dot([((O, NEG), (P, REAL0))]), 3: J}
         # second step, line only, through (X3,Y3,Z3) and (q2x, qy)

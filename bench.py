@@ -125,6 +125,28 @@ def cpu_reference_rate(cid, inputs, n_sample, budget_s, nthreads=0):
     return done / dt, nt, done, dt
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun warnings) may write to fd 1; the contract is ONE JSON line on stdout.
+    Everything written to fd 1 from here on goes to stderr; emit() writes the JSON line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference_arm(args):
     """CPU arm: the reference's algorithm on the host cores, same metric/unit/config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -160,7 +182,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -173,6 +195,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -328,7 +351,7 @@ def main():
                 "api": "b200_pairing2_batch(host buffers, B200_FEXP)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -148,7 +148,9 @@ struct Vm {
     }
     // Montgomery reduction of a wide value T < 4 p R (T[0..2N), top word zero) -> canonical residue T / R mod p.
     // Word-sliding reduction on an even / odd split of T: no data movement, the window offsets are compile-time.
-    static B200_HD void redc(E1& r, const uint32_t* Tw) {
+    // skip2p: the caller guarantees T < p R, so the result is below 2p before the final subtraction (microcode header
+    // flag HDR_SKIP2P, set per phase by the compiler from the number of accumulated products)
+    static B200_HD void redc(E1& r, const uint32_t* Tw, bool skip2p) {
         uint32_t X[AW], Y[AW];
 #pragma unroll
         for (int k = 0; k < 2 * N; k += 2) { X[k] = Tw[k]; X[k + 1] = 0; Y[k] = Tw[k + 1]; Y[k + 1] = 0; }
@@ -187,7 +189,7 @@ struct Vm {
 #pragma unroll
         for (int k = 1; k < N - 1; k++) r.l[k] = addc_cc(Xw[k], Yw[k + 1]);
         r.l[N - 1] = addc(Xw[N - 1], Yw[N]);
-        cond_sub_kp(r, 1);
+        if (!skip2p) cond_sub_kp(r, 1);
         cond_sub_kp(r, 0);
     }
     // acc (even aligned, full-size words above) += v_even * m, carry rippled one word up
@@ -317,8 +319,9 @@ struct Vm {
                     wide_add(IM, v);
                 }
             }
-            redc(res.c0, RE);
-            redc(res.c1, IM);
+            const bool skip2p = (hdr >> 18) & 1;
+            redc(res.c0, RE, skip2p);
+            redc(res.c1, IM, skip2p);
             if (scale != 1) { mul_small(res.c0, res.c0, scale); mul_small(res.c1, res.c1, scale); }
         } else {
             T::f2_zero(res);

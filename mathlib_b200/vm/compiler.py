@@ -33,6 +33,16 @@ REAL0, REAL1 = 4, 8                        # B operand only: use component 0 / 1
 C_ABS, C_B1, C_B2, C_B3, C_CONST = 0, 1, 2, 3, 4
 
 KIND_NOP, KIND_DOT, KIND_LIN, KIND_INV = 0, 1, 2, 3
+HDR_SKIP2P = 1 << 18     # header flag: the phase's dot products are short enough that redc's output is already < 2p
+
+# a DOT of nt terms feeds redc with T < 2 nt p^2 (6 nt p^2 when BETA = -5); redc returns T/R + (< p), so for
+# nt < R / (2p) [R / (6p)] the result is below 2p and the interpreter may drop the conditional subtraction of 2p.
+# Set per curve by programs.build_all (BLS12-381: 4, BN254: 2, BLS12-377: 6).
+_skip2p_terms = [0]
+
+
+def set_skip2p_terms(n):
+    _skip2p_terms[0] = n
 OP_WORDS = 12            # header + 6 terms + 4 lin + 1 spare  (fixed size keeps the interpreter trivial)
 
 
@@ -266,6 +276,7 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
         # the widest dot product of the phase: every lane runs the same multi-operand product variant (zero padded),
         # so lanes with fewer terms do not serialise against the others
         pmax = max([len(v.terms) for v in vs if v.kind == 'dot'] + [0])
+        skip2p = HDR_SKIP2P if 0 < pmax <= _skip2p_terms[0] else 0
         for v in lanes:
             w = [0] * OP_WORDS
             if v is not None:
@@ -275,7 +286,7 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
                 alt = enc_operand(loc(v.alt)) if v.alt is not None else 0
                 assert 1 <= v.scale <= 7
                 w[0] = (k | (nt << 4) | (nl << 8) | (v.scale << 12) | ((1 if v.halve else 0) << 15) | (v.pred << 16) |
-                        (pmax << 20))
+                        (pmax << 20) | skip2p)
                 w[1] = enc_operand(loc(v)) | (alt << 16)
                 for t, (a, am, b, bm) in enumerate(v.terms):
                     w[2 + t] = enc_operand(loc(a)) | (enc_operand(loc(b)) << 11) | (am << 22) | (bm << 26)

@@ -11,8 +11,8 @@ Slot maps
 The formulas are the ones of csrc/pairing.cuh (SURVEY A.5 doubling / addition steps, sparse line slots, Granger-Scott
 squaring); tests/test_vm_programs.py checks every compiled program against the oracle.
 """
-from .compiler import (ref, const, dot, lin, inv, mul, sqr, compile_program, NEG, CONJ, XI, DBL, REAL0, REAL1,
-                       C_ABS, C_B1, C_B2, C_B3, C_CONST)
+from .compiler import (ref, const, dot, lin, inv, mul, sqr, compile_program, set_skip2p_terms, NEG, CONJ, XI, DBL, REAL0,
+                       REAL1, C_ABS, C_B1, C_B2, C_B3, C_CONST)
 
 T_BASE, Q_BASE = 12, 18
 # per-curve slot file: BLS12 curves (96-byte slots): 48 slots, 5 Fp12 registers for the final exponentiation;
@@ -459,6 +459,8 @@ def build_all(curve_name):
     cv = CURVES[curve_name]
     _cfg['nslots'], _cfg['nregs'] = SLOTCFG[curve_name]
     _cfg['qstride'] = 3 if cv.family == 'bn' else 2
+    # R/(2p) = 4.92 (BLS12-381), 2.65 (BN254); R/(6p) = 25 (BLS12-377, BETA = -5): see compiler.HDR_SKIP2P
+    set_skip2p_terms({'BLS381': 4, 'BN254': 0, 'BLS377': 6}[curve_name])      # BN254: no measurable gain, left off
     progs = {}
     for np_ in (1, 2):
         progs['INIT%d' % np_] = prog_init(np_)

@@ -311,8 +311,10 @@ def main():
         "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one vm_pairing_kernel<BLS381,2> launch at this batch size
         # (ncu capture profiles/r1_bench_launches.md); the algorithmic HBM bytes are 1,152 B per check
-        "traffic": 28.5e6 * n / 65536,
-        "traffic_detail": {"dram_bytes_per_launch_at_65536_checks": 28.5e6, "algorithmic_bytes_per_launch": 1152 * n,
+        "traffic": 39.7e6 * n / 65536,
+        "traffic_detail": {"dram_bytes_per_launch_at_65536_checks": 39.7e6, "algorithmic_bytes_per_launch": 1152 * n,
+                           "note": "39.3 MB read (the 37.7 MB of inputs, after the L2 flush) + 0.4 MB written: the 37.7 MB "
+                                   "of outputs are still in L2 when the kernel ends",
                            "source": "profiles/r1_bench_launches.md"},
         "kernel": "vm_pairing_kernel<BLS381,2> (warp-cooperative VM: Miller loop x2 + final exponentiation fused)",
         "note": "integer-multiply roofline (SURVEY 8d): algorithmic MAC32 = checks/s x %d m x 300; peak = measured "

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200math.so")
+LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "libb200math.so"))     # B200_LIB: development override
 
 # flags (include/b200.h)
 FEXP = 0x1

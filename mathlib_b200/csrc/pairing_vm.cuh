@@ -414,14 +414,16 @@ struct VmDriver {
 // Block shape.  BLS12 curves: 4 warps (20 groups) per block, two blocks per SM -- the operand-scanning wide product needs
 // ~200 registers, so 8 resident warps is the register-file limit (12 warps need <= 168 registers, which the slower
 // product-scanning variant reaches: measured 103.7 ms vs 99.9 ms per 65,536 checks for this shape).
+#ifndef B200_VM_WARPS_MAX
 #define B200_VM_WARPS_MAX 4
+#endif
 #ifndef B200_VM_WARPS_BN
 #define B200_VM_WARPS_BN 11
 #endif
 // BN254 (8-limb operands, ~160 registers): one block of 11 warps per SM for the Pairing / FExp kernels (55 slot files +
 // the core microcode = 220 KB); the kernels that stage the full microcode (fixed-Q, Gt ops) use 10
 template <class C> __host__ __device__ constexpr int vm_warps() { return C::N == 8 ? B200_VM_WARPS_BN : B200_VM_WARPS_MAX; }
-template <class C> __host__ __device__ constexpr int vm_warps_x() { return C::N == 8 ? 10 : B200_VM_WARPS_MAX; }
+template <class C> __host__ __device__ constexpr int vm_warps_x() { return C::N == 8 ? 10 : 4; }
 #define B200_VM_GROUPS_PER_WARP 5
 #define B200_VM_GROUP_PAD 4          // words; staggers the groups across shared-memory banks
 

@@ -318,27 +318,53 @@ struct JacOps {
 
 template <class C>
 __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_t* out, uint32_t flags) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // One warp.  The Horner chain is serial in the doublings, but inside a doubling three field products are independent
+    // at each of the first two levels: lanes 0..2 take one each (every lane keeps a full copy of the point and repeats
+    // the cheap additions), results are exchanged through shared memory.  4 product latencies per doubling instead of 8.
+    if (blockIdx.x != 0) return;
     typedef G1Ops<C> G;
     typedef FpOps<C> F;
     typedef JacOps<C> J;
+    typedef typename F::E E;
+    __shared__ E sh[3];
+    const int lane = threadIdx.x & 31;
+    const int sel = lane < 2 ? lane : 2;
+    // r0, r1, r2 = a0*b0, a1*b1, a2*b2, one product per lane
+    auto par3 = [&](E& r0, E& r1, E& r2, const E& a0, const E& b0, const E& a1, const E& b1, const E& a2, const E& b2) {
+        E a = sel == 0 ? a0 : (sel == 1 ? a1 : a2);
+        E b = sel == 0 ? b0 : (sel == 1 ? b1 : b2);
+        E r;
+        F::mul(r, a, b);
+        if (lane < 3) sh[lane] = r;
+        __syncwarp();
+        r0 = sh[0]; r1 = sh[1]; r2 = sh[2];
+        __syncwarp();
+    };
     typename G::Pt acc;
     G::set_inf(acc);
     for (int w = pl.W - 1; w >= 0; w--) {
-        if (!G::is_inf(acc)) {
-            // XYZZ (X, Y, ZZ, ZZZ) -> Jacobian with Z = ZZZ/ZZ would need an inversion; use the equivalent
-            // representative (X*ZZ^2... ) : scale to Z' = ZZ*ZZZ:  x = X/ZZ = (X*ZZ*ZZZ^2)/Z'^2, y = Y/ZZZ = (Y*ZZ^3*ZZZ^2)/Z'^3
+        if (!G::is_inf(acc) && pl.W > 1) {
+            // XYZZ (X, Y, ZZ, ZZZ) -> Jacobian with Z' = ZZ*ZZZ:  x = X/ZZ = (X*ZZ*ZZZ^2)/Z'^2, y = Y/ZZZ = (Y*ZZ^3*ZZZ^2)/Z'^3
             typename J::Pt j;
-            typename F::E zz2, zzz2, t;
-            F::sqr(zzz2, acc.zzz);
-            F::sqr(zz2, acc.zz);
-            F::mul(t, acc.x, acc.zz);
-            F::mul(j.x, t, zzz2);
-            F::mul(t, acc.y, zz2);
-            F::mul(t, t, acc.zz);
-            F::mul(j.y, t, zzz2);
-            F::mul(j.z, acc.zz, acc.zzz);
-            for (int k = 0; k < pl.c; k++) J::dbl(j);
+            E zz2, zzz2, t, u;
+            par3(zzz2, zz2, j.z, acc.zzz, acc.zzz, acc.zz, acc.zz, acc.zz, acc.zzz);
+            par3(t, u, zz2, acc.x, acc.zz, acc.y, zz2, zz2, zz2);           // t = X*ZZ, u = Y*ZZ^2 (third product unused)
+            F::mul(u, u, acc.zz);
+            par3(j.x, j.y, zz2, t, zzz2, u, zzz2, t, t);
+            for (int k = 0; k < pl.c; k++) {                                // dbl-2009-l, a = 0
+                E A, B, T, Cc, D, Fv, Ev, s;
+                par3(A, B, T, j.x, j.x, j.y, j.y, j.y, j.z);
+                F::add(s, j.x, B);
+                F::dbl(Ev, A); F::add(Ev, Ev, A);
+                par3(Cc, D, Fv, B, B, s, s, Ev, Ev);
+                F::sub(D, D, A); F::sub(D, D, Cc); F::dbl(D, D);
+                F::dbl(j.z, T);
+                F::sub(j.x, Fv, D); F::sub(j.x, j.x, D);
+                F::sub(s, D, j.x);
+                F::mul(s, Ev, s);
+                F::dbl(Cc, Cc); F::dbl(Cc, Cc); F::dbl(Cc, Cc);
+                F::sub(j.y, s, Cc);
+            }
             // back to XYZZ: ZZ = Z^2, ZZZ = Z^3
             acc.x = j.x; acc.y = j.y;
             F::sqr(acc.zz, j.z);
@@ -349,7 +375,7 @@ __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_
     }
     typename G::Aff r;
     G::to_affine(r, acc);
-    Codec<C>::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);
+    if (lane == 0) Codec<C>::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);
 }
 
 #endif  // __CUDACC__

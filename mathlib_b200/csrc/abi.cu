@@ -226,7 +226,7 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
     b->size_hist = (uint32_t*)take(2 * 1024 * 4);
     b->buckets = take(nb * vt->xyzz_size);
     b->chunks = take((size_t)pl.W * pl.nchunks * vt->xyzz_size);
-    b->windows = take((size_t)pl.W * vt->xyzz_size);
+    b->windows = take((size_t)pl.W * 9 * vt->xyzz_size);      // W window sums + 8 partial sums per window
     if (scalars_dev) *scalars_dev = take(n * 32);
     if (pts_in_dev) *pts_in_dev = take(pts_in_bytes);
     if (out_dev) *out_dev = take(2 * (size_t)vt->fp_bytes);

@@ -363,8 +363,15 @@ struct Launch {
         msm_reduce_kernel<C><<<blocks_for((size_t)pt.W * pt.nchunks, 128), 128, 0, s>>>(pt, (const Pt*)b.buckets,
                                                                                         (Pt*)b.chunks);
         B200_COUNT_LAUNCH();
-        const int wt = pt.nchunks >= 1024 ? 256 : 64;
-        msm_window_sum_kernel<C><<<pt.W, wt, wt * sizeof(Pt), s>>>(pt, (const Pt*)b.chunks, (Pt*)b.windows);
+        if (pt.nchunks >= 1024) {
+            // two stages: 8 partial sums per window (buffer behind the W window slots), then the windows
+            Pt* part = (Pt*)b.windows + pl.W;
+            msm_window_sum_kernel<C><<<pt.W * 8, 64, 64 * sizeof(Pt), s>>>(pt.nchunks / 8, (const Pt*)b.chunks, part);
+            msm_window_sum_kernel<C><<<pt.W, 32, 32 * sizeof(Pt), s>>>(8, (const Pt*)part, (Pt*)b.windows);
+            B200_COUNT_LAUNCH();
+        } else {
+            msm_window_sum_kernel<C><<<pt.W, 64, 64 * sizeof(Pt), s>>>(pt.nchunks, (const Pt*)b.chunks, (Pt*)b.windows);
+        }
         B200_COUNT_LAUNCH();
         msm_final_kernel<C><<<1, 32, 0, s>>>(pt, (const Pt*)b.windows, out, flags);
         B200_COUNT_LAUNCH();

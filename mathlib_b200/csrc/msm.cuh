@@ -262,17 +262,19 @@ msm_reduce_kernel(MsmPlan pl, const G1XYZZ<C::N>* buckets, G1XYZZ<C::N>* chunk_o
     chunk_out[id] = acc;
 }
 
-// one block per window: sum of nchunks chunk results -> window_out[w]
+// segment sums: out[seg] = sum of in[seg*count .. seg*count + count), one block per segment (shared-memory tree).
+// The per-window sum of the chunk results runs in two stages (W*8 segments, then W) so that it spreads over 128 SMs
+// instead of 16.
 template <class C>
-__global__ void msm_window_sum_kernel(MsmPlan pl, const G1XYZZ<C::N>* chunk_in, G1XYZZ<C::N>* window_out) {
+__global__ void msm_window_sum_kernel(int count, const G1XYZZ<C::N>* in, G1XYZZ<C::N>* out) {
     extern __shared__ uint32_t shraw[];
     typedef G1Ops<C> G;
     typename G::Pt* sh = reinterpret_cast<typename G::Pt*>(shraw);
-    int w = blockIdx.x;
+    const size_t seg = blockIdx.x;
     typename G::Pt acc;
     G::set_inf(acc);
-    for (int j = threadIdx.x; j < pl.nchunks; j += blockDim.x) {
-        typename G::Pt v = chunk_in[(size_t)w * pl.nchunks + j];
+    for (int j = threadIdx.x; j < count; j += blockDim.x) {
+        typename G::Pt v = in[seg * count + j];
         G::add(acc, v);
     }
     sh[threadIdx.x] = acc;
@@ -285,7 +287,7 @@ __global__ void msm_window_sum_kernel(MsmPlan pl, const G1XYZZ<C::N>* chunk_in, 
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) window_out[w] = sh[0];
+    if (threadIdx.x == 0) out[seg] = sh[0];
 }
 
 // Horner over the windows, then affine normalisation + store.  One thread: this is a pure dependency chain of

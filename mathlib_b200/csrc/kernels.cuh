@@ -181,9 +181,12 @@ fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err)
 }
 
 #define B200_G1_THREADS 128
+#ifndef B200_G1_MIN_BLOCKS
+#define B200_G1_MIN_BLOCKS 4        // 16 warps per SM: caps the kernels at 128 registers (measured against 2 blocks at 186)
+#endif
 
 template <class C>
-__global__ void __launch_bounds__(B200_G1_THREADS)
+__global__ void __launch_bounds__(B200_G1_THREADS, B200_G1_MIN_BLOCKS)
 g1_mul_kernel(size_t n, const uint8_t* pts, const uint8_t* scalars, uint8_t* out, uint32_t flags, int* err) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -202,7 +205,7 @@ g1_mul_kernel(size_t n, const uint8_t* pts, const uint8_t* scalars, uint8_t* out
 }
 
 template <class C>
-__global__ void __launch_bounds__(B200_G1_THREADS)
+__global__ void __launch_bounds__(B200_G1_THREADS, B200_G1_MIN_BLOCKS)
 g1_mul2_kernel(size_t n, const uint8_t* P, const uint8_t* es, const uint8_t* Q, const uint8_t* fs, uint8_t* out,
                uint32_t flags, int* err) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -87,6 +87,15 @@ def test_full_size_properties(m):
     g1a, g2a, g1b, g2b, expect = rand_inputs(m, 3, n, seed=55)
     ver = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP | m.OUT_UNITY_ONLY)
     assert (np.frombuffer(ver, dtype=np.uint8) == expect).all()
+    # the same 65,536 checks against a resident line table of the distinct G2 arguments: same verdicts
+    qsz = c.G2ByteSize
+    rows, ra = {}, []
+    for i in range(n):
+        ra.append(rows.setdefault(g2a[i * qsz:(i + 1) * qsz], len(rows)))
+    table = list(rows) + [c.GenG2.Bytes()]
+    h = c.G2LinesUpload(b"".join(table), len(table))
+    assert c.Pairing2FixedBatch(h, g1a, ra, g1b, [len(table) - 1] * n, n, m.FEXP | m.OUT_UNITY_ONLY) == ver
+    c.G2LinesFree(h)
     c5 = m.Curves[5]
     nm = 1 << 18
     rnd = np.random.default_rng(9)

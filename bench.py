@@ -319,7 +319,9 @@ def main():
         "kernel": "vm_pairing_kernel<BLS381,2> (warp-cooperative VM: Miller loop x2 + final exponentiation fused)",
         # from the committed ncu capture of this kernel (not measured in this run): north_star's roofline evidence
         "ncu": {"sm__pipe_fmaheavy_cycles_active_pct": 59.2, "smsp__issue_active_pct": 37.5,
-                "source": "profiles/r1_pairing_vm_ncu.md"},
+                "source": "profiles/r1_pairing_vm_ncu.md",
+                "miller_loop_only_sm__pipe_fmaheavy_cycles_active_pct": 62.0,
+                "miller_loop_source": "profiles/r1_miller_loop_ncu.md"},
         "note": "integer-multiply roofline (SURVEY 8d): algorithmic MAC32 = checks/s x %d m x 300; peak = measured "
                 "IMAD.WIDE.U32 issue rate (tools/imad_peak.cu, profiles/peaks_r1.json). HBM traffic is "
                 "1,152 B per check (<0.01%% of HBM bandwidth), so no HBM roofline applies." % M_PER_OP["bls381_pairing2_fexp"],

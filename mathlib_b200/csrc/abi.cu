@@ -801,7 +801,7 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
     if (n) {
         if (flags & B200_DEVICE_PTRS) {
             CU(vt->msm_points(n, (const uint8_t*)pts, d_pts, kernel_flags(flags), device_err_flag(dev), t_stream));
-            if (rows > 1) CU(vt->msm_tables(n, tp.c, tp.W, n, d_pts, t_stream));
+            if (rows > 1) CU(vt->msm_tables(n, tp, n, d_pts, t_stream));
             CU(cudaStreamSynchronize(t_stream));
         } else {
             WsGuard g(dev);
@@ -811,7 +811,7 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
             CU(cudaMemcpyAsync(w.buf, pts, n * g1sz, cudaMemcpyHostToDevice, w.stream));
             CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
             CU(vt->msm_points(n, w.buf, d_pts, kernel_flags(flags), w.d_err, w.stream));
-            if (rows > 1) CU(vt->msm_tables(n, tp.c, tp.W, n, d_pts, w.stream));
+            if (rows > 1) CU(vt->msm_tables(n, tp, n, d_pts, w.stream));
             int h_err = 0;
             CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
             CU(cudaStreamSynchronize(w.stream));

@@ -63,7 +63,7 @@ struct CurveVTable {
     // points -> Montgomery affine array (for MSM / resident bases)
     cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
     // resident window tables: tab[w*stride + i] = 2^(c*w) * tab[i]
-    cudaError_t (*msm_tables)(size_t n, int c, int W, size_t stride, void* tab, cudaStream_t s);
+    cudaError_t (*msm_tables)(size_t n, const MsmPlan& pl, size_t stride, void* tab, cudaStream_t s);
     // MSM over prepared points
     cudaError_t (*msm)(size_t n, const void* prepared_pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
                        const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s);
@@ -321,9 +321,9 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
-    static cudaError_t msm_tables(size_t n, int c, int W, size_t stride, void* tab, cudaStream_t s) {
-        if (n == 0 || W < 2) return cudaSuccess;
-        msm_tables_kernel<C><<<blocks_for(n, 128), 128, 0, s>>>(n, c, W, stride, (G1Affine<C::N>*)tab);
+    static cudaError_t msm_tables(size_t n, const MsmPlan& pl, size_t stride, void* tab, cudaStream_t s) {
+        if (n == 0 || pl.W < 2) return cudaSuccess;
+        msm_tables_kernel<C><<<blocks_for(n, 128), 128, 0, s>>>(n, pl, stride, (G1Affine<C::N>*)tab);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }

@@ -17,6 +17,7 @@
 // disappears.
 // The result is a canonical group element, so the order of additions inside a bucket does not matter.
 #pragma once
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace b200 {
@@ -27,19 +28,49 @@ struct MsmPlan {
     int B;          // buckets per window = 2^(c-1)
     int chunk;      // buckets per reduce thread
     int nchunks;    // B / chunk
-    int tables;     // 1: points come from a resident window table, tab[w*stride + i] = 2^(c*w) * P_i  (no Horner tail)
+    int tables;     // 1: points come from a resident window table, tab[w*stride + i] = 2^start(w) * P_i  (no Horner tail)
     unsigned long long stride;
+    int narrow;     // the top `narrow` windows are c-1 bits wide (see msm_plan)
 };
+
+// Window w covers scalar bits [start, start + width).  The W windows tile the scalar exactly: the lower W - narrow ones
+// are c bits wide, the top `narrow` ones c - 1 bits.  (Equal c-bit windows would leave a top window of bits mod c bits --
+// or only the carry -- whose few buckets collect n / 2^(bits mod c) points each and serialise the accumulation.)
+static inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+int msm_win_width(const MsmPlan& p, int w) { return w < p.W - p.narrow ? p.c : p.c - 1; }
+static inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+int msm_win_start(const MsmPlan& p, int w) {
+    const int full = p.W - p.narrow;
+    return w <= full ? w * p.c : full * p.c + (w - full) * (p.c - 1);
+}
 
 static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int c = lg - 3;
+    // window size: measured on B200 (tools/msm_sizes_probe.py).  Below ~2^17 points the run time is the latency of the
+    // serial tails (reduce / window sums / Horner), which shrink with FEWER windows, so c is larger than the work-optimal
+    // lg - 3; from 2^17 on the bucket accumulation dominates and c = 16.
+    static const int bias = getenv("B200_MSM_C_BIAS") ? atoi(getenv("B200_MSM_C_BIAS")) : 0;     // development knob
+    int c = lg <= 13 ? (lg + 1 > 7 ? lg + 1 : 7) : (lg == 14 ? 15 : (lg == 15 ? 14 : (lg == 16 ? 15 : 16)));
+    c += bias;
     if (c < 2) c = 2;
     if (c > 16) c = 16;
     MsmPlan p;
     p.c = c;
     p.W = scalar_bits / c + 1;
+    // widths in {c, c-1} summing to scalar_bits, at least one narrow window on top: its digit plus the incoming carry
+    // is at most 2^(c-1) = B, so the top window needs no carry out
+    p.narrow = p.W * c - scalar_bits;
+    if (p.narrow > p.W) {                 // cannot happen for c <= 16 and 253..255-bit orders; keep the plan valid anyway
+        p.W = (scalar_bits + c - 2) / (c - 1);
+        p.narrow = p.W;
+    }
     p.B = 1 << (c - 1);
     p.chunk = p.B >= 1024 ? 16 : (p.B >= 32 ? 8 : 1);
     p.nchunks = p.B / p.chunk;
@@ -87,14 +118,14 @@ __global__ void msm_digits_kernel(size_t n, const uint8_t* scalars, MsmPlan pl, 
     scalar_reduce<C>(k);
     k[8] = 0;
     uint32_t carry = 0;
-    const uint32_t mask = (1u << pl.c) - 1;
     for (int w = 0; w < pl.W; w++) {
-        int bit = w * pl.c;
+        const int bit = msm_win_start(pl, w), cw = msm_win_width(pl, w);
         uint32_t lo = k[bit >> 5] >> (bit & 31);
-        if ((bit & 31) + pl.c > 32 && (bit >> 5) + 1 < 9) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
-        uint32_t d = (bit < 256 ? (lo & mask) : 0) + carry;
+        if ((bit & 31) + cw > 32 && (bit >> 5) + 1 < 9) lo |= k[(bit >> 5) + 1] << (32 - (bit & 31));
+        uint32_t d = (bit < 256 ? (lo & ((1u << cw) - 1)) : 0) + carry;
         uint32_t neg = 0;
-        if (d > (uint32_t)pl.B) { d = (1u << pl.c) - d; neg = 1; carry = 1; } else carry = 0;
+        // signed digits: fold d > 2^(cw-1) to d - 2^cw with a carry into the next window; never on the top window
+        if (w + 1 < pl.W && d > (1u << (cw - 1))) { d = (1u << cw) - d; neg = 1; carry = 1; } else carry = 0;
         uint32_t packed = d ? ((d << 1) | neg) : 0;
         digits[(size_t)w * n + i] = packed;
         if (d) atomicAdd(&counts[(size_t)w * pl.B + (d - 1)], 1u);
@@ -202,15 +233,15 @@ msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uin
 // one inversion each); runs once per upload.
 template <class C>
 __global__ void __launch_bounds__(128)
-msm_tables_kernel(size_t n, int c, int W, size_t stride, G1Affine<C::N>* tab) {
+msm_tables_kernel(size_t n, MsmPlan pl, size_t stride, G1Affine<C::N>* tab) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     typedef G1Ops<C> G;
     typename G::Aff a = tab[i];
-    for (int w = 1; w < W; w++) {
+    for (int w = 1; w < pl.W; w++) {
         typename G::Pt p;
         G::dbl_affine(p, a);
-        for (int k = 1; k < c; k++) G::dbl(p);
+        for (int k = 1; k < msm_win_width(pl, w - 1); k++) G::dbl(p);
         G::to_affine(a, p);
         tab[(size_t)w * stride + i] = a;
     }
@@ -353,7 +384,7 @@ __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_
             par3(t, u, zz2, acc.x, acc.zz, acc.y, zz2, zz2, zz2);           // t = X*ZZ, u = Y*ZZ^2 (third product unused)
             F::mul(u, u, acc.zz);
             par3(j.x, j.y, zz2, t, zzz2, u, zzz2, t, t);
-            for (int k = 0; k < pl.c; k++) {                                // dbl-2009-l, a = 0
+            for (int k = 0; k < msm_win_width(pl, w); k++) {                // dbl-2009-l, a = 0
                 E A, B, T, Cc, D, Fv, Ev, s;
                 par3(A, B, T, j.x, j.x, j.y, j.y, j.y, j.z);
                 F::add(s, j.x, B);

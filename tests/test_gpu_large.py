@@ -58,7 +58,9 @@ def test_g1_mul_random_vs_cpu_oracle(m, cid):
     assert out2 == orc.g1_mul2_batch(cid, n, g1a, ks, g1b, ks2)
 
 
-@pytest.mark.parametrize("cid,n", [(5, 1), (5, 7), (5, 1000), (5, 1 << 14), (1, 1 << 14), (4, 1 << 13), (3, 300)])
+@pytest.mark.parametrize("cid,n", [(5, 1), (5, 7), (5, 1000), (5, 1 << 14), (1, 1 << 14), (4, 1 << 13), (3, 300),
+                                   # every window size of msm_plan (c = 7..16, mixed c / c-1 bit windows) on all three orders
+                                   (4, 50), (1, 3000), (5, (1 << 13) + 1), (5, 1 << 15), (1, 1 << 16), (4, 1 << 17)])
 def test_msm_random_vs_cpu_oracle(m, cid, n):
     from oracle import cpu_binding as orc
     c = m.Curves[cid]

@@ -227,6 +227,10 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
     b->buckets = take(nb * vt->xyzz_size);
     b->chunks = take((size_t)pl.W * pl.nchunks * vt->xyzz_size);
     b->windows = take((size_t)pl.W * 9 * vt->xyzz_size);      // W window sums + 8 partial sums per window
+    b->max_heavy = (uint32_t)(((size_t)pl.W * n) / 512);       // B200_MSM_SEG = 512 points per segment
+    b->heavy_n = (uint32_t*)take(4);
+    b->heavy_items = take((size_t)b->max_heavy * 8);
+    b->heavy_partial = take((size_t)b->max_heavy * vt->xyzz_size);
     if (scalars_dev) *scalars_dev = take(n * 32);
     if (pts_in_dev) *pts_in_dev = take(pts_in_bytes);
     if (out_dev) *out_dev = take(2 * (size_t)vt->fp_bytes);

@@ -28,6 +28,10 @@ struct MsmBuffers {            // device pointers carved out of one workspace sl
     void* buckets;             // W * B * sizeof(G1XYZZ)
     void* chunks;              // W * nchunks * sizeof(G1XYZZ)
     void* windows;             // W * sizeof(G1XYZZ)
+    uint32_t* heavy_n;         // number of heavy items (device counter)
+    void* heavy_items;         // max_heavy * sizeof(MsmHeavyItem)
+    void* heavy_partial;       // max_heavy * sizeof(G1XYZZ)
+    uint32_t max_heavy;        // W * n / B200_MSM_SEG
 };
 
 struct CurveVTable {
@@ -351,9 +355,25 @@ struct Launch {
         msm_size_scan_kernel<<<1, B200_MSM_SIZE_BINS, 0, s>>>(b.size_hist, b.size_hist + B200_MSM_SIZE_BINS);
         msm_size_scatter_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist + B200_MSM_SIZE_BINS, b.perm);
         B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
+        if (b.max_heavy) {
+            if ((e = cudaMemsetAsync(b.heavy_n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
+            msm_heavy_list_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.heavy_n, (MsmHeavyItem*)b.heavy_items,
+                                                                      b.max_heavy);
+            B200_COUNT_LAUNCH();
+        }
         msm_accumulate_kernel<C><<<blocks_for(nb, 128), 128, 0, s>>>(n, pl, (const G1Affine<C::N>*)pts, b.offsets,
                                                                     b.counts, b.sorted, b.perm, (Pt*)b.buckets);
         B200_COUNT_LAUNCH();
+        if (b.max_heavy) {
+            // long runs (more than B200_MSM_SEG points in one bucket): split over extra threads; empty for uniform scalars
+            const unsigned hb = blocks_for(b.max_heavy, 128);
+            msm_heavy_accumulate_kernel<C><<<hb, 128, 0, s>>>(n, pl, (const G1Affine<C::N>*)pts, b.offsets, b.counts, b.sorted,
+                                                              b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
+                                                              (Pt*)b.heavy_partial);
+            msm_heavy_merge_kernel<C><<<hb, 128, 0, s>>>(b.counts, b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
+                                                         (const Pt*)b.heavy_partial, (Pt*)b.buckets);
+            B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
+        }
         MsmPlan pt = pl;                             // plan of the tail (one window when the bucket arrays were folded)
         if (pl.tables && pl.W > 1) {
             msm_fold_kernel<C><<<blocks_for(pl.B, 128), 128, 0, s>>>(pl, (Pt*)b.buckets);

@@ -200,6 +200,65 @@ static __global__ void msm_size_scatter_kernel(size_t nb, const uint32_t* counts
     perm[pos] = (uint32_t)t;
 }
 
+// Long runs (skewed scalars: many equal digits) would serialise on one thread.  A bucket accumulates at most B200_MSM_SEG
+// points in msm_accumulate_kernel; every further segment of B200_MSM_SEG points becomes an item (bucket, segment) of a
+// list built on the device, is summed by its own thread, and the partial sums are added to the bucket afterwards.  With
+// uniform scalars the list is empty and the two extra kernels exit at once.
+#define B200_MSM_SEG 512
+struct MsmHeavyItem { uint32_t bucket, seg; };
+static __global__ void msm_heavy_list_kernel(size_t nb, const uint32_t* counts, uint32_t* heavy_n, MsmHeavyItem* items,
+                                             uint32_t max_items) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    const uint32_t cnt = counts[t];
+    if (cnt <= B200_MSM_SEG) return;
+    const uint32_t k = (cnt - 1) / B200_MSM_SEG;                       // extra segments 1..k
+    const uint32_t pos = atomicAdd(heavy_n, k);
+    for (uint32_t s = 1; s <= k && pos + s - 1 < max_items; s++) items[pos + s - 1] = {(uint32_t)t, s};
+}
+template <class C>
+__global__ void __launch_bounds__(128, 2)
+msm_heavy_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
+                            const uint32_t* sorted, const uint32_t* heavy_n, const MsmHeavyItem* items, G1XYZZ<C::N>* partial) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= *heavy_n) return;
+    typedef G1Ops<C> G;
+    const MsmHeavyItem it = items[id];
+    const size_t t = it.bucket, w = t / pl.B;
+    if (pl.tables) pts += w * pl.stride;
+    const uint32_t lo = it.seg * B200_MSM_SEG;
+    uint32_t hi = lo + B200_MSM_SEG;
+    if (hi > counts[t]) hi = counts[t];
+    const uint32_t* run = sorted + w * n + offsets[t];
+    typename G::Pt acc;
+    G::set_inf(acc);
+    for (uint32_t j = lo; j < hi; j++) {
+        const uint32_t e = run[j];
+        typename G::Aff a = pts[e >> 1];
+        if (e & 1) FpOps<C>::neg(a.y, a.y);
+        G::madd(acc, a);
+    }
+    partial[id] = acc;
+}
+// one thread per heavy bucket (the thread of its first item): the items of a bucket are contiguous in the list
+template <class C>
+__global__ void __launch_bounds__(128, 2)
+msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const MsmHeavyItem* items, const G1XYZZ<C::N>* partial,
+                       G1XYZZ<C::N>* buckets) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= *heavy_n) return;
+    const MsmHeavyItem it = items[id];
+    if (it.seg != 1) return;
+    typedef G1Ops<C> G;
+    const uint32_t k = (counts[it.bucket] - 1) / B200_MSM_SEG;
+    typename G::Pt acc = buckets[it.bucket];
+    for (uint32_t s = 0; s < k; s++) {
+        typename G::Pt v = partial[id + s];
+        G::add(acc, v);
+    }
+    buckets[it.bucket] = acc;
+}
+
 template <class C>
 __global__ void __launch_bounds__(128, 2)
 msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
@@ -212,6 +271,7 @@ msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uin
     if (pl.tables) pts += w * pl.stride;
     const uint32_t* run = sorted + w * n + offsets[t];
     uint32_t cnt = counts[t];
+    if (cnt > B200_MSM_SEG) cnt = B200_MSM_SEG;          // the rest of a long run is split over msm_heavy_* threads
     typename G::Pt acc;
     G::set_inf(acc);
     // software prefetch: the gather of point j+1 (index read + 2*FpBytes random read out of L2/HBM) is issued before

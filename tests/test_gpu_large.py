@@ -79,6 +79,19 @@ def test_msm_skewed_scalars(m):
     g1a, _, _, _, _ = rand_inputs(m, 5, n, seed=401)
     ks = b"".join((((1 << 63) - 1) if i % 3 else 5).to_bytes(32, "big") for i in range(n))
     assert c.MsmBatch(g1a, ks, n) == orc.g1_msm(5, n, g1a, ks)
+    # long runs: 2^16 points, all scalars equal (every point of a window lands in ONE bucket: 128 segments of 512), and a
+    # mix where a third of the scalars are equal; runs longer than B200_MSM_SEG are split over extra threads (msm.cuh)
+    import time
+    n = 1 << 16
+    g1a, _, _, _, _ = rand_inputs(m, 5, n, seed=402)
+    rnd = random.Random(12)
+    k0 = rnd.randrange(c.order)
+    for ks in (k0.to_bytes(32, "big") * n,
+               b"".join((k0 if i % 3 == 0 else rnd.randrange(c.order)).to_bytes(32, "big") for i in range(n))):
+        t0 = time.perf_counter()
+        got = c.MsmBatch(g1a, ks, n)
+        assert time.perf_counter() - t0 < 2.0          # a single thread walking 65,536 points would take ~1 s per window
+        assert got == orc.g1_msm(5, n, g1a, ks)
 
 
 def test_full_size_properties(m):

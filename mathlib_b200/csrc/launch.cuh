@@ -11,6 +11,7 @@
 #include "pairing_vm.cuh"
 #include "g2.cuh"
 #include "points.cuh"
+#include "g1_p3.cuh"
 
 namespace b200 {
 
@@ -300,9 +301,21 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
+    // batches up to this size run three lanes per operation (g1_p3.cuh).  Measured: 1,000 Mul 2.5 ms against 3.4 ms, but
+    // 12,500 Mul 5.6 ms against 4.3 ms -- the exchange and the repeated additions cost more than the shorter chain saves
+    // once the one-lane kernel has enough warps, so only really small calls take this path.
+    static size_t p3_max() {
+        static long v = getenv("B200_G1_P3_MAX") ? atol(getenv("B200_G1_P3_MAX")) : 2048;
+        return (size_t)v;
+    }
     static cudaError_t g1_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
                               cudaStream_t s) {
         if (n == 0) return cudaSuccess;
+        if (n <= p3_max()) {
+            g1_mul_p3_kernel<C, 1><<<blocks_for(n, B200_P3_OPS_PER_BLOCK), B200_P3_THREADS, 0, s>>>(n, pts, k, pts, k, out, flags, err);
+            B200_COUNT_LAUNCH();
+            return cudaGetLastError();
+        }
         g1_mul_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, g1_smem_pad(), s>>>(n, pts, k, out, flags, err);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
@@ -310,6 +323,11 @@ struct Launch {
     static cudaError_t g1_mul2(size_t n, const uint8_t* P, const uint8_t* e, const uint8_t* Q, const uint8_t* f,
                                uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
         if (n == 0) return cudaSuccess;
+        if (n <= p3_max()) {
+            g1_mul_p3_kernel<C, 2><<<blocks_for(n, B200_P3_OPS_PER_BLOCK), B200_P3_THREADS, 0, s>>>(n, P, e, Q, f, out, flags, err);
+            B200_COUNT_LAUNCH();
+            return cudaGetLastError();
+        }
         g1_mul2_kernel<C><<<blocks_for(n, B200_G1_THREADS), B200_G1_THREADS, g1_smem_pad(), s>>>(n, P, e, Q, f, out, flags, err);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();

@@ -72,7 +72,8 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
         p.narrow = p.W;
     }
     p.B = 1 << (c - 1);
-    p.chunk = p.B >= 1024 ? 16 : (p.B >= 32 ? 8 : 1);
+    static const int chunk_knob = getenv("B200_MSM_CHUNK") ? atoi(getenv("B200_MSM_CHUNK")) : 0;    // development knob
+    p.chunk = p.B >= 1024 ? (chunk_knob ? chunk_knob : 16) : (p.B >= 32 ? 8 : 1);
     p.nchunks = p.B / p.chunk;
     p.tables = 0;
     p.stride = 0;

@@ -157,6 +157,77 @@ extern "C" int he_vm_pairing(int curve, int np, const uint8_t* g1a, const uint8_
     return t_vm_pair<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
 }
 
+// fixed-Q pairing on the host: line tables of the G2 arguments (precompute_lines), then miller_fixed -- the control flow of
+// vm_lines_kernel + vm_pairing_fixed_kernel
+template <class C> static int t_vm_pair_fixed(int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
+                                              const uint8_t* g2b, uint8_t* out, int fexp) {
+    constexpr int N = C::N;
+    typedef VmTables<C> TB;
+    std::vector<uint32_t> kb((size_t)VM_KBANK * 2 * N);
+    for (int i = 0; i < VM_KBANK; i++) vm_fill_kbank<C>(kb.data() + (size_t)i * 2 * N, i);
+    const size_t rowsz = (size_t)VmDriver<C>::nlines() * 3 * 2 * N;
+    std::vector<uint32_t> rows[2];
+    bool qinf[2] = {false, false};
+    int err = 0;
+    for (int k = 0; k < np; k++) {
+        std::vector<uint32_t> slots((size_t)TB::NSLOTS * 2 * N, 0u);
+        VmDriver<C> D;
+        D.ctx.slots = slots.data(); D.ctx.kbank = kb.data(); D.ctx.live = 3;
+        D.words = TB::host_words(); D.dir = TB::host_dir(); D.role = 0;
+        unsigned z = 0;
+        for (int r = 2; r < VM_G; r++) z |= (unsigned)D.load_coord(r, 0, nullptr, k ? g2b : g2a, false, &err) << r;
+        qinf[k] = (z & 60u) == 60u;
+        rows[k].assign(rowsz, 0u);
+        D.precompute_lines(rows[k].data());
+    }
+    if (err) return 1;
+    std::vector<uint32_t> slots((size_t)TB::NSLOTS * 2 * N, 0u);
+    VmDriver<C> D;
+    D.ctx.slots = slots.data(); D.ctx.kbank = kb.data();
+    D.words = TB::host_words(); D.dir = TB::host_dir(); D.role = 0;
+    unsigned m0 = 0, m1 = 0;
+    for (int r = 0; r < 2; r++) {
+        m0 |= (unsigned)D.load_coord(r, 0, g1a, nullptr, false, &err) << r;
+        if (np == 2) m1 |= (unsigned)D.load_coord(r, 1, g1b, nullptr, false, &err) << r;
+    }
+    if (err) return 1;
+    const bool dead0 = ((m0 & 3u) == 3u) || qinf[0];
+    const bool dead1 = np == 2 ? (((m1 & 3u) == 3u) || qinf[1]) : true;
+    D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
+    const uint32_t* r1 = np == 2 ? rows[1].data() : rows[0].data();
+    uint32_t fb = np == 1 ? D.template miller_fixed<1>(rows[0].data(), r1) : D.template miller_fixed<2>(rows[0].data(), r1);
+    if (fexp) fb = D.final_exp(fb);
+    for (int r = 0; r < VM_G; r++) D.store_coeff(r, fb, out, false);
+    return 0;
+}
+extern "C" int he_vm_pairing_fixed(int curve, int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
+                                   const uint8_t* g2b, uint8_t* out, int fexp) {
+    if (curve == 0) return t_vm_pair_fixed<BN254>(np, g1a, g2a, g1b, g2b, out, fexp);
+    if (curve == 1) return t_vm_pair_fixed<BLS381>(np, g1a, g2a, g1b, g2b, out, fexp);
+    return t_vm_pair_fixed<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
+}
+// Gt.Exp ladder on the host (VmDriver::gt_exp)
+template <class C> static int t_vm_gt_exp(const uint8_t* gt, const uint8_t* k, uint8_t* out) {
+    constexpr int N = C::N;
+    typedef VmTables<C> TB;
+    std::vector<uint32_t> slots((size_t)TB::NSLOTS * 2 * N, 0u), kb((size_t)VM_KBANK * 2 * N);
+    for (int i = 0; i < VM_KBANK; i++) vm_fill_kbank<C>(kb.data() + (size_t)i * 2 * N, i);
+    VmDriver<C> D;
+    D.ctx.slots = slots.data(); D.ctx.kbank = kb.data(); D.ctx.live = 3;
+    D.words = TB::host_words(); D.dir = TB::host_dir(); D.role = 0;
+    int err = 0;
+    for (int r = 0; r < VM_G; r++) D.load_coeff(r, 0, gt, false, &err);
+    if (err) return 1;
+    uint32_t fb = D.gt_exp(k, VmDriver<C>::scalar_bitlen(k));
+    for (int r = 0; r < VM_G; r++) D.store_coeff(r, fb, out, false);
+    return 0;
+}
+extern "C" int he_vm_gt_exp(int curve, const uint8_t* gt, const uint8_t* k, uint8_t* out) {
+    if (curve == 0) return t_vm_gt_exp<BN254>(gt, k, out);
+    if (curve == 1) return t_vm_gt_exp<BLS381>(gt, k, out);
+    return t_vm_gt_exp<BLS377>(gt, k, out);
+}
+
 // mul_dot<T>: r = sum a[t]*b[t] / R mod p  (operands as 3 consecutive Fp each)
 template <class C> static void t_dot(int T, const uint32_t* a, const uint32_t* b, uint32_t* o) {
     typedef FpOps<C> F; typename F::E x[3], y[3], z;

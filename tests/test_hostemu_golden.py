@@ -132,3 +132,24 @@ def test_fp_inverse_and_dot(hostemu):
                 o = (ctypes.c_uint32 * n)()
                 hostemu.he_fp_dot(ci, T, arr(a), arr(b), o)
                 assert val(o) == sum(a[t] * b[t] for t in range(T)) * pow(R, -1, P.p) % P.p
+
+
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_vm_fixed_q_and_gt_exp_on_host(hostemu, cid):
+    """The C++ control flow of the fixed-Q kernels (precompute_lines + miller_fixed) and of the Gt.Exp ladder, host-emulated:
+    fixed-Q results equal the golden Pairing / Pairing2 bytes (raw and exponentiated, infinity cases included), Gt.Exp
+    equals the golden vectors."""
+    v = load_vectors(cid)
+    ec = EMU_CURVE[cid]
+    n = 32 if cid == 1 else 48
+    out = ctypes.create_string_buffer(12 * n)
+    for case in v["pairing"]:
+        args = (bytes.fromhex(case["g1"]), bytes.fromhex(case["g2"]), None, None)
+        assert hostemu.he_vm_pairing_fixed(ec, 1, *args, out, 0) == 0 and out.raw.hex() == case["pairing"]
+    for case in v["pairing2"]:
+        args = [bytes.fromhex(case[k]) for k in ("g1a", "g2a", "g1b", "g2b")]
+        assert hostemu.he_vm_pairing_fixed(ec, 2, *args, out, 0) == 0 and out.raw.hex() == case["pairing2"]
+        assert hostemu.he_vm_pairing_fixed(ec, 2, *args, out, 1) == 0 and out.raw.hex() == case["fexp"]
+    for case in v["gt_exp"][::3]:
+        assert hostemu.he_vm_gt_exp(ec, bytes.fromhex(case["a"]), bytes.fromhex(case["k"]), out) == 0
+        assert out.raw.hex() == case["out"]

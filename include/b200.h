@@ -9,7 +9,8 @@
  *    thread-local message.  The library never aborts the process; the Go wrapper turns a non-zero return
  *    into the same panic the reference drivers raise (reference driver/gurvy/bn254.go:249-251).
  *  - Every function is re-entrant; concurrent calls that share read-only inputs are legal (the reference
- *    benchmarks call one curve from many goroutines: perf_test.go:392-405).
+ *    benchmarks call one curve from many goroutines: perf_test.go:392-405).  b200_init / b200_shutdown must not run
+ *    concurrently with other calls.
  *  - Host buffers belong to the caller and are only read / written during the call (cgo pointer rules).
  *  - `curve` is the mathlib CurveID (reference math.go:70-103): 1 BN254, 3 BLS12_381 (kilic semantics),
  *    4 BLS12_377_GURVY, 5 BLS12_381_GURVY, 6 BLS12_381_BBS (kilic semantics), 7 BLS12_381_BBS_GURVY.
@@ -53,7 +54,9 @@ extern "C" {
 #define B200_OUT_MONT 0x4u       /* group/Gt outputs are MONT limbs instead of BYTES */
 #define B200_OUT_UNITY_ONLY 0x8u /* pairing / fexp: write one byte per item: 1 if the result is 1 (Gt.IsUnity), else 0 */
 #define B200_DEVICE_PTRS 0x10u   /* all buffers are device pointers on the current device (no copies, async on the
-                                    stream set with b200_set_stream; caller synchronises) */
+                                    stream set with b200_set_stream; caller synchronises).  The call returns before its
+                                    kernels ran, so a rejected input cannot fail it with B200_ERR_ENCODING: see
+                                    b200_take_error(). */
 #define B200_BASES_TABLES 0x20u  /* b200_bases_upload: also store 2^(c*w) * P_i for every Pippenger window w (W x the
                                     memory, one-time cost of c*(W-1) doublings per point); MSMs against the handle then
                                     skip the Horner tail.  Ignored (plain bases kept) when the table would exceed 1/4 of
@@ -77,6 +80,15 @@ int b200_device_count(void);
 int b200_set_device(int device);
 /* Per calling thread: CUDA stream (cudaStream_t as void*) used with B200_DEVICE_PTRS; NULL = default stream. */
 int b200_set_stream(void* cuda_stream);
+
+/* Error reporting of B200_DEVICE_PTRS calls.  With host buffers a non-canonical coordinate (or any other rejected
+   input) fails the call with B200_ERR_ENCODING.  With device pointers the failure is PER ITEM: the offending item's
+   output is written as all-zero bytes (verdict 0 with B200_OUT_UNITY_ONLY -- never a stale or passing value), every
+   other item of the batch is computed normally, and a per-device flag is raised.  b200_take_error synchronises the
+   calling thread's stream, stores 1 in *had_error if any B200_DEVICE_PTRS call on the current device raised the flag
+   since the last take (0 otherwise) and clears it.  Row indices of b200_pairing*_fixed_batch outside the table are
+   reported the same way. */
+int b200_take_error(int* had_error);
 
 /* sizes in bytes of the BYTES / MONT encodings for a curve (FpBytes = 32 or 48) */
 int b200_fp_bytes(int curve);

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "b200_device_count": (_int, []),
     "b200_set_device": (_int, [_int]),
     "b200_set_stream": (_int, [_vp]),
+    "b200_take_error": (_int, [ctypes.POINTER(_int)]),
     "b200_fp_bytes": (_int, [_int]),
     "b200_pairing_batch": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
     "b200_pairing2_batch": (_int, [_int, _sz, _vp, _vp, _vp, _vp, _vp, _u32]),

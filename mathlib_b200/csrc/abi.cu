@@ -25,8 +25,12 @@ thread_local int t_device = -1;          // -1: not pinned by b200_set_device
 thread_local cudaStream_t t_stream = nullptr;
 
 std::mutex g_mu;
-bool g_inited = false;
-std::vector<int> g_devices;
+std::atomic<bool> g_inited{false};
+std::vector<int> g_devices;          // written under g_mu by b200_init; readers take a snapshot with devices()
+std::vector<int> devices() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_devices;
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -98,24 +102,31 @@ void ws_release(Workspace* w) {
 struct WsGuard {
     Workspace* w;
     explicit WsGuard(int dev) : w(ws_acquire(dev)) {}
-    ~WsGuard() { if (w) ws_release(w); }
+    // an error return may leave copies or kernels in flight on the workspace's stream: drain it before the slab goes
+    // back to the pool (free when the stream is already idle, which is the normal return path)
+    ~WsGuard() {
+        if (!w) return;
+        cudaSetDevice(w->dev);
+        cudaStreamSynchronize(w->stream);
+        ws_release(w);
+    }
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 int ensure_init() {
-    if (g_inited) return 0;
+    if (g_inited.load(std::memory_order_acquire)) return 0;
     return b200_init(0);
 }
-int current_device() { return t_device >= 0 ? t_device : g_devices[0]; }
+int current_device() { return t_device >= 0 ? t_device : devices()[0]; }
 
 // devices a host-buffer batch call is split over
 std::vector<int> split_devices(size_t n, size_t min_per_dev) {
-    std::vector<int> d;
-    if (t_device >= 0 || g_devices.size() == 1 || n < 2 * min_per_dev) { d.push_back(current_device()); return d; }
-    size_t k = g_devices.size();
+    std::vector<int> all = devices(), d;
+    if (t_device >= 0 || all.size() == 1 || n < 2 * min_per_dev) { d.push_back(current_device()); return d; }
+    size_t k = all.size();
     while (k > 1 && n / k < min_per_dev) k--;
-    d.assign(g_devices.begin(), g_devices.begin() + k);
+    d.assign(all.begin(), all.begin() + k);
     return d;
 }
 
@@ -174,7 +185,10 @@ int staged_call(int dev, size_t lo, size_t hi, std::vector<Piece> ins, void* out
     return 0;
 }
 
-int* device_err_flag(int dev) {      // scratch flag for DEVICE_PTRS calls (never read back)
+// Error flag of the B200_DEVICE_PTRS calls of one device.  Those calls are asynchronous, so a rejected input cannot
+// fail them: the kernels write a defined output for the offending item (zero element / verdict 0) and raise this flag;
+// b200_take_error() reads and clears it.
+int* device_err_flag(int dev) {
     static std::map<int, int*> flags;
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = flags.find(dev);
@@ -285,7 +299,7 @@ int b200_init(uint32_t device_mask) {
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
     if (e != cudaSuccess || cnt == 0) {
-        g_inited = false;
+        g_inited.store(false);
         return fail(B200_ERR_NOGPU, "no CUDA device available (%s); libb200math has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
@@ -293,7 +307,7 @@ int b200_init(uint32_t device_mask) {
     for (int i = 0; i < cnt && i < 32; i++)
         if (device_mask == 0 || (device_mask >> i) & 1) g_devices.push_back(i);
     if (g_devices.empty()) return fail(B200_ERR_ARG, "device mask 0x%x selects none of the %d devices", device_mask, cnt);
-    g_inited = true;
+    g_inited.store(true, std::memory_order_release);
     return 0;
 }
 
@@ -313,14 +327,14 @@ void b200_shutdown(void) {
     g_bases.clear();
     for (auto& kv : g_lines) { cudaSetDevice(kv.second.dev); cudaFree(kv.second.lines); cudaFree(kv.second.qinf); }
     g_lines.clear();
-    g_inited = false;
+    g_inited.store(false);
 }
 
 const char* b200_last_error(void) { return t_err.c_str(); }
 
 int b200_device_count(void) {
     if (ensure_init()) return 0;
-    return (int)g_devices.size();
+    return (int)devices().size();
 }
 
 int b200_set_device(int device) {
@@ -334,6 +348,21 @@ int b200_set_device(int device) {
 
 int b200_set_stream(void* cuda_stream) {
     t_stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int b200_take_error(int* had_error) {
+    if (int rc = ensure_init()) return rc;
+    if (!had_error) return fail(B200_ERR_ARG, "null buffer");
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    int* flag = device_err_flag(dev);
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, t_stream));
+    CU(cudaMemsetAsync(flag, 0, sizeof(int), t_stream));
+    CU(cudaStreamSynchronize(t_stream));
+    *had_error = h ? 1 : 0;
+    if (h) t_err = "a B200_DEVICE_PTRS call rejected an input (not a canonical element encoding, or a row index out of range)";
     return 0;
 }
 
@@ -496,13 +525,26 @@ int b200_g1_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags)
 
 static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool prepared, const void* scalars,
                            void* out, uint32_t flags, const Bases* bs = nullptr) {
-    // device-pointer MSM: the workspace comes from the pool and is held until the stream is synchronised by the
-    // caller, so it is acquired per thread and kept (thread-local) instead of being released.
-    thread_local std::map<int, Workspace*> t_ws;
+    // device-pointer MSM: the call returns while its kernels are still queued, so the scratch slab cannot go back to
+    // the pool at return.  It is kept per (calling thread, device, stream) -- two streams never share a slab, MSMs
+    // issued on one stream are ordered by the stream -- and returned to the pool, after draining the stream, when the
+    // thread ends (cgo threads come and go).
+    struct Held {
+        std::map<std::pair<int, cudaStream_t>, Workspace*> ws;
+        ~Held() {
+            for (auto& kv : ws) {
+                if (!kv.second) continue;
+                cudaSetDevice(kv.first.first);
+                cudaStreamSynchronize(kv.first.second);
+                ws_release(kv.second);
+            }
+        }
+    };
+    thread_local Held t_held;
     const CurveVTable* vt = ci.vt;
     int dev = current_device();
     CU(cudaSetDevice(dev));
-    Workspace*& w = t_ws[dev];
+    Workspace*& w = t_held.ws[std::make_pair(dev, t_stream)];
     if (!w) w = ws_acquire(dev);
     if (!w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
     MsmPlan pl = resident_plan(vt, bs, n);
@@ -516,7 +558,7 @@ static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool 
     msm_carve(vt, pl, n, need_points, w->buf, &b, nullptr, nullptr, 0, nullptr);
     const void* prep = pts;
     if (need_points && n) {
-        CU(vt->msm_points(n, (const uint8_t*)pts, b.points, kernel_flags(flags), w->d_err, t_stream));
+        CU(vt->msm_points(n, (const uint8_t*)pts, b.points, kernel_flags(flags), device_err_flag(dev), t_stream));
         prep = b.points;
     }
     CU(vt->msm(n, prep, (const uint8_t*)scalars, (uint8_t*)out, kernel_flags(flags), pl, b, t_stream));
@@ -704,8 +746,8 @@ static int pairing_fixed_common(uint64_t handle, int np, size_t n, const void* g
     const size_t osz = (flags & B200_OUT_UNITY_ONLY) ? 1 : 12 * (size_t)vt->fp_bytes;
     CU(cudaSetDevice(ln.dev));
     if (flags & B200_DEVICE_PTRS) {
-        CU(vt->pairing_fixed(np, n, (const uint8_t*)g1a, qa, (const uint8_t*)g1b, qb, ln.lines, ln.qinf, (uint8_t*)out, kf,
-                             device_err_flag(ln.dev), t_stream));
+        CU(vt->pairing_fixed(np, n, (const uint8_t*)g1a, qa, (const uint8_t*)g1b, qb, ln.lines, ln.qinf, (uint32_t)ln.n_q,
+                             (uint8_t*)out, kf, device_err_flag(ln.dev), t_stream));
         return 0;
     }
     // row indices arrive from the host: reject out-of-range rows before they become device addresses
@@ -722,7 +764,7 @@ static int pairing_fixed_common(uint64_t handle, int np, size_t n, const void* g
                            return vt->pairing_fixed(np, m, p[0].dev, ia >= 0 ? (const uint32_t*)p[ia].dev : nullptr,
                                                     np == 2 ? p[1].dev : nullptr,
                                                     ib >= 0 ? (const uint32_t*)p[ib].dev : nullptr, ln.lines, ln.qinf,
-                                                    d_out, kf, d_err, s);
+                                                    (uint32_t)ln.n_q, d_out, kf, d_err, s);
                        });
 }
 
@@ -791,7 +833,12 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
     const CurveVTable* vt = ci.vt;
     int dev = current_device();
     CU(cudaSetDevice(dev));
-    void* d_pts = nullptr;
+    struct DevMem {            // freed on every early return; release() hands the pointer to the handle table
+        void* p = nullptr;
+        ~DevMem() { if (p) cudaFree(p); }
+        void* release() { void* q = p; p = nullptr; return q; }
+    } mem;
+    void*& d_pts = mem.p;
     MsmPlan tp = msm_plan(n ? n : 1, vt->scalar_bits);
     int rows = 1;
     if ((flags & B200_BASES_TABLES) && n && tp.W > 1) {
@@ -809,9 +856,9 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
             CU(cudaStreamSynchronize(t_stream));
         } else {
             WsGuard g(dev);
-            if (!g.w) { cudaFree(d_pts); return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev); }
+            if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
             Workspace& w = *g.w;
-            if (int rc = w.reserve(n * g1sz)) { cudaFree(d_pts); return rc; }
+            if (int rc = w.reserve(n * g1sz)) return rc;
             CU(cudaMemcpyAsync(w.buf, pts, n * g1sz, cudaMemcpyHostToDevice, w.stream));
             CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
             CU(vt->msm_points(n, w.buf, d_pts, kernel_flags(flags), w.d_err, w.stream));
@@ -819,12 +866,12 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
             int h_err = 0;
             CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
             CU(cudaStreamSynchronize(w.stream));
-            if (h_err) { cudaFree(d_pts); return fail(B200_ERR_ENCODING, "input is not a canonical element encoding"); }
+            if (h_err) return fail(B200_ERR_ENCODING, "input is not a canonical element encoding");
         }
     }
     std::lock_guard<std::mutex> lk(g_mu);
     uint64_t h = g_next_handle++;
-    g_bases[h] = {curve, dev, n, d_pts, rows > 1 ? tp.c : 0, rows > 1 ? tp.W : 0};
+    g_bases[h] = {curve, dev, n, mem.release(), rows > 1 ? tp.c : 0, rows > 1 ? tp.W : 0};
     *handle = h;
     return 0;
 }

@@ -104,10 +104,10 @@ g1_mul_p3_kernel(size_t n, const uint8_t* P, const uint8_t* es, const uint8_t* Q
         CD::g1_load(b.x, b.y, Q + it * CD::g1_size(), flags & FLAG_IN_MONT, &e);
         CD::scalar_load(kf, fs + it * 32);
     }
-    if (__ballot_sync(0xffffffffu, active && e != 0)) {
-        if (lane == 0) atomicExch(err, 1);
-        return;
-    }
+    // a rejected encoding fails its own operation only (flag raised, all-zero output); g1_load has zeroed the point, so
+    // the three lanes run the ladder on infinity in lock-step with the rest of the warp
+    const bool bad = active && e != 0;
+    if (bad && X.sel == 0) atomicExch(err, 1);
     typename G::Pt acc;
     G::set_inf(acc);
     if (C::FAMILY == FAMILY_BLS12) {
@@ -148,7 +148,10 @@ g1_mul_p3_kernel(size_t n, const uint8_t* P, const uint8_t* es, const uint8_t* Q
     }
     typename G::Aff r;
     G::to_affine(r, acc);
-    if (active && X.sel == 0) CD::g1_store(out + item * CD::g1_size(), r.x, r.y, flags & FLAG_OUT_MONT);
+    if (active && X.sel == 0) {
+        if (bad) CD::store_zero(out + item * CD::g1_size(), CD::g1_size());
+        else CD::g1_store(out + item * CD::g1_size(), r.x, r.y, flags & FLAG_OUT_MONT);
+    }
 }
 #endif  // __CUDACC__
 

@@ -151,7 +151,7 @@ g2_mul_kernel(size_t n, const uint8_t* pts, const uint8_t* scalars, uint8_t* out
     int e = 0;
     typename G::Aff a;
     CD::g2_load(a, pts + i * CD::g2_size(), flags & FLAG_IN_MONT, &e);
-    if (e) { atomicExch(err, 1); return; }
+    if (e) { atomicExch(err, 1); CD::store_zero(out + i * CD::g2_size(), CD::g2_size()); return; }
     uint32_t k[8];
     CD::scalar_load(k, scalars + i * 32);
     typename G::Pt acc;
@@ -174,7 +174,7 @@ __global__ void g2_sum_kernel(size_t n, const uint8_t* pts, uint8_t* out, uint32
         CD::g2_load(a, pts + i * CD::g2_size(), flags & FLAG_IN_MONT, &e);
         G::madd(acc, a);
     }
-    if (e) { atomicExch(err, 1); return; }
+    if (e) { atomicExch(err, 1); Codec<C>::store_zero(out, Codec<C>::g2_size()); return; }
     typename G::Aff r;
     G::to_affine(r, acc);
     G2Codec<C>::g2_store(out, r, flags & FLAG_OUT_MONT);

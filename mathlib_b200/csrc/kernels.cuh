@@ -79,6 +79,10 @@ struct Codec {
         fp_from_bytes(x, s, (uint8_t)~flag_mask(), err);
         fp_from_bytes(y, s + FB, 0xFF, err);
     }
+    // defined output of an item whose input was rejected (B200_ERR_ENCODING): all-zero bytes
+    static B200_HD void store_zero(uint8_t* d, size_t bytes) {
+        for (size_t i = 0; i < bytes; i++) d[i] = 0;
+    }
     static B200_HD void g1_store(uint8_t* d, const Fp<N>& x, const Fp<N>& y, bool mont) {
         if (mont) {
             fp_to_mont_words((uint32_t*)d, x);
@@ -157,7 +161,11 @@ pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* 
         CD::g1_load(P[NP - 1].x, P[NP - 1].y, g1b + i * CD::g1_size(), in_mont, &e);
         CD::g2_load(Q[NP - 1], g2b + i * CD::g2_size(), in_mont, &e);
     }
-    if (e) { atomicExch(err, 1); return; }
+    if (e) {
+        atomicExch(err, 1);
+        if (flags & FLAG_UNITY) out[i] = 0; else CD::store_zero(out + i * CD::gt_size(), CD::gt_size());
+        return;
+    }
     Fp12<N> f;
     PO::template miller_loop<NP>(f, P, Q);
     if (flags & FLAG_FEXP) PO::final_exp(f, f);
@@ -174,7 +182,11 @@ fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err)
     int e = 0;
     Fp12<C::N> f;
     CD::gt_load(f, in + i * CD::gt_size(), flags & FLAG_IN_MONT, &e);
-    if (e) { atomicExch(err, 1); return; }
+    if (e) {
+        atomicExch(err, 1);
+        if (flags & FLAG_UNITY) out[i] = 0; else CD::store_zero(out + i * CD::gt_size(), CD::gt_size());
+        return;
+    }
     if (flags & FLAG_FEXP) PairingOps<C>::final_exp(f, f);
     if (flags & FLAG_UNITY) out[i] = Tower<C>::f12_is_one(f) ? 1 : 0;
     else CD::gt_store(out + i * CD::gt_size(), f, flags & FLAG_OUT_MONT);
@@ -195,7 +207,7 @@ g1_mul_kernel(size_t n, const uint8_t* pts, const uint8_t* scalars, uint8_t* out
     int e = 0;
     typename G::Aff a;
     CD::g1_load(a.x, a.y, pts + i * CD::g1_size(), flags & FLAG_IN_MONT, &e);
-    if (e) { atomicExch(err, 1); return; }
+    if (e) { atomicExch(err, 1); CD::store_zero(out + i * CD::g1_size(), CD::g1_size()); return; }
     uint32_t k[8];
     CD::scalar_load(k, scalars + i * 32);
     typename G::Pt acc;
@@ -216,7 +228,7 @@ g1_mul2_kernel(size_t n, const uint8_t* P, const uint8_t* es, const uint8_t* Q, 
     typename G::Aff a, b;
     CD::g1_load(a.x, a.y, P + i * CD::g1_size(), flags & FLAG_IN_MONT, &e);
     CD::g1_load(b.x, b.y, Q + i * CD::g1_size(), flags & FLAG_IN_MONT, &e);
-    if (e) { atomicExch(err, 1); return; }
+    if (e) { atomicExch(err, 1); CD::store_zero(out + i * CD::g1_size(), CD::g1_size()); return; }
     uint32_t ke[8], kf[8];
     CD::scalar_load(ke, es + i * 32);
     CD::scalar_load(kf, fs + i * 32);
@@ -240,7 +252,7 @@ __global__ void g1_sum_kernel(size_t n, const uint8_t* pts, uint8_t* out, uint32
         CD::g1_load(a.x, a.y, pts + i * CD::g1_size(), flags & FLAG_IN_MONT, &e);
         G::madd(acc, a);
     }
-    if (e) { atomicExch(err, 1); return; }
+    if (e) { atomicExch(err, 1); CD::store_zero(out, CD::g1_size()); return; }
     typename G::Aff r;
     G::to_affine(r, acc);
     CD::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);

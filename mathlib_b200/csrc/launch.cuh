@@ -60,8 +60,8 @@ struct CurveVTable {
     cudaError_t (*lines_build)(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, uint32_t flags, int* err,
                                cudaStream_t s);
     cudaError_t (*pairing_fixed)(int np, size_t n, const uint8_t* g1a, const uint32_t* qa_idx, const uint8_t* g1b,
-                                 const uint32_t* qb_idx, const uint32_t* lines, const uint8_t* qinf, uint8_t* out,
-                                 uint32_t flags, int* err, cudaStream_t s);
+                                 const uint32_t* qb_idx, const uint32_t* lines, const uint8_t* qinf, uint32_t n_q,
+                                 uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
     // point decompression (op 0) / compression (1) / validation (2) batches, g2 = 0 / 1
     cudaError_t (*point_codec)(int g2, int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err,
                                cudaStream_t s);
@@ -84,10 +84,15 @@ static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned
 
 template <class C>
 struct Launch {
-    // development knob: unused dynamic shared memory caps the resident blocks of the G1 kernels (measured: no gain)
+    // development knob (-DB200_DEV_KNOBS builds only): unused dynamic shared memory caps the resident blocks of the G1
+    // kernels (measured: no gain)
     static size_t g1_smem_pad() {
+#if defined(B200_DEV_KNOBS)
         static long v = getenv("B200_G1_SMEM_PAD") ? atol(getenv("B200_G1_SMEM_PAD")) : 0;
         return (size_t)v;
+#else
+        return 0;
+#endif
     }
     static cudaError_t pairing(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
                                const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
@@ -106,9 +111,11 @@ struct Launch {
         if (variant == 3) { B200_LAUNCH_VARIANT(256, 3); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
         if (variant == 4) { B200_LAUNCH_VARIANT(256, 4); B200_COUNT_LAUNCH(); return cudaGetLastError(); }
 #endif
-        static int legacy = getenv("B200_PAIR_LEGACY") ? atoi(getenv("B200_PAIR_LEGACY")) : 0;
-        // thread-per-pairing kernel (pairing.cuh): kept as an independent cross-check of the VM kernel
+#if defined(B200_PAIR_LEGACY_BUILD)
+        // thread-per-pairing kernel (pairing.cuh): an independent cross-check of the VM kernel, only in builds made with
+        // -DB200_PAIR_LEGACY_BUILD (it is 600 KB of code and a minute of compile time; not in the product library)
         // (65,536 BN254 Pairing+FExp: 63.5 ms here vs 58.7 ms on the VM; BLS12-381 Pairing2+FExp: 128 ms vs 100 ms)
+        static int legacy = getenv("B200_PAIR_LEGACY") ? atoi(getenv("B200_PAIR_LEGACY")) : 0;
         if (legacy) {
             unsigned nb = blocks_for(n, B200_PAIR_THREADS);
             if (np == 1) pairing_kernel<C, 1><<<nb, B200_PAIR_THREADS, 0, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err);
@@ -116,6 +123,7 @@ struct Launch {
             B200_COUNT_LAUNCH();
             return cudaGetLastError();
         }
+#endif
         return vm_pairing(np, n, g1a, g2a, g1b, g2b, out, flags, err, s);
     }
     // batches that cannot fill every SM with full-size blocks use the 4-warp variant (20 products per block)
@@ -196,12 +204,14 @@ struct Launch {
     }
     static cudaError_t fexp(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
         if (n == 0) return cudaSuccess;
+#if defined(B200_PAIR_LEGACY_BUILD)
         static int legacy = getenv("B200_PAIR_LEGACY") ? atoi(getenv("B200_PAIR_LEGACY")) : 0;
         if (legacy) {
             fexp_kernel<C><<<blocks_for(n, B200_PAIR_THREADS), B200_PAIR_THREADS, 0, s>>>(n, in, out, flags, err);
             B200_COUNT_LAUNCH();
             return cudaGetLastError();
         }
+#endif
         const uint32_t* d_words = nullptr;
         const VmDirEntry* d_dir = nullptr;
         cudaError_t e = vm_setup(&d_words, &d_dir);
@@ -237,26 +247,26 @@ struct Launch {
     }
     template <int W>
     static void fixed_launch(int np, size_t n, const uint8_t* g1a, const uint32_t* qa, const uint8_t* g1b, const uint32_t* qb,
-                             const uint32_t* lines, const uint8_t* qinf, uint8_t* out, uint32_t flags, int* err,
+                             const uint32_t* lines, const uint8_t* qinf, uint32_t n_q, uint8_t* out, uint32_t flags, int* err,
                              const uint32_t* d_words, const VmDirEntry* d_dir, cudaStream_t s) {
         const unsigned gpb = W * B200_VM_GROUPS_PER_WARP;
         const unsigned nb = (unsigned)((n + gpb - 1) / gpb);
         const size_t smem = vm_smem_bytes<C, W>();
         if (np == 1)
-            vm_pairing_fixed_kernel<C, 1, W><<<nb, W * 32, smem, s>>>(n, g1a, qa, g1a, qa, lines, qinf, out, flags, err, d_words, d_dir);
+            vm_pairing_fixed_kernel<C, 1, W><<<nb, W * 32, smem, s>>>(n, g1a, qa, g1a, qa, lines, qinf, n_q, out, flags, err, d_words, d_dir);
         else
-            vm_pairing_fixed_kernel<C, 2, W><<<nb, W * 32, smem, s>>>(n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir);
+            vm_pairing_fixed_kernel<C, 2, W><<<nb, W * 32, smem, s>>>(n, g1a, qa, g1b, qb, lines, qinf, n_q, out, flags, err, d_words, d_dir);
     }
     static cudaError_t pairing_fixed(int np, size_t n, const uint8_t* g1a, const uint32_t* qa, const uint8_t* g1b,
-                                     const uint32_t* qb, const uint32_t* lines, const uint8_t* qinf, uint8_t* out,
-                                     uint32_t flags, int* err, cudaStream_t s) {
+                                     const uint32_t* qb, const uint32_t* lines, const uint8_t* qinf, uint32_t n_q,
+                                     uint8_t* out, uint32_t flags, int* err, cudaStream_t s) {
         if (n == 0) return cudaSuccess;
         const uint32_t* d_words = nullptr;
         const VmDirEntry* d_dir = nullptr;
         cudaError_t e = vm_setup(&d_words, &d_dir);
         if (e != cudaSuccess) return e;
-        if (small_batch(n)) fixed_launch<B200_VM_WARPS_SMALL>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
-        else fixed_launch<vm_warps_x<C>()>(np, n, g1a, qa, g1b, qb, lines, qinf, out, flags, err, d_words, d_dir, s);
+        if (small_batch(n)) fixed_launch<B200_VM_WARPS_SMALL>(np, n, g1a, qa, g1b, qb, lines, qinf, n_q, out, flags, err, d_words, d_dir, s);
+        else fixed_launch<vm_warps_x<C>()>(np, n, g1a, qa, g1b, qb, lines, qinf, n_q, out, flags, err, d_words, d_dir, s);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
@@ -305,8 +315,12 @@ struct Launch {
     // 12,500 Mul 5.6 ms against 4.3 ms -- the exchange and the repeated additions cost more than the shorter chain saves
     // once the one-lane kernel has enough warps, so only really small calls take this path.
     static size_t p3_max() {
+#if defined(B200_DEV_KNOBS)
         static long v = getenv("B200_G1_P3_MAX") ? atol(getenv("B200_G1_P3_MAX")) : 2048;
         return (size_t)v;
+#else
+        return 2048;
+#endif
     }
     static cudaError_t g1_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
                               cudaStream_t s) {

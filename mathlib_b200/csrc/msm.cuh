@@ -56,7 +56,11 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
     // window size: measured on B200 (tools/msm_sizes_probe.py).  Below ~2^17 points the run time is the latency of the
     // serial tails (reduce / window sums / Horner), which shrink with FEWER windows, so c is larger than the work-optimal
     // lg - 3; from 2^17 on the bucket accumulation dominates and c = 16.
+#if defined(B200_DEV_KNOBS)
     static const int bias = getenv("B200_MSM_C_BIAS") ? atoi(getenv("B200_MSM_C_BIAS")) : 0;     // development knob
+#else
+    const int bias = 0;
+#endif
     int c = lg <= 13 ? (lg + 1 > 7 ? lg + 1 : 7) : (lg == 14 ? 15 : (lg == 15 ? 14 : (lg == 16 ? 15 : 16)));
     c += bias;
     if (c < 2) c = 2;
@@ -72,7 +76,11 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
         p.narrow = p.W;
     }
     p.B = 1 << (c - 1);
+#if defined(B200_DEV_KNOBS)
     static const int chunk_knob = getenv("B200_MSM_CHUNK") ? atoi(getenv("B200_MSM_CHUNK")) : 0;    // development knob
+#else
+    const int chunk_knob = 0;
+#endif
     p.chunk = p.B >= 1024 ? (chunk_knob ? chunk_knob : 16) : (p.B >= 32 ? 8 : 1);
     p.nchunks = p.B / p.chunk;
     p.tables = 0;

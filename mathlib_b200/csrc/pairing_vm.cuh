@@ -399,6 +399,14 @@ struct VmDriver {
             for (int i = 0; i < N; i++) dst[a * N + i] = v.l[i];
         }
     }
+    // defined output of an item whose input was rejected: lane r zeroes its share (2 Fp) of the Gt element
+    B200_HD void store_zero_coeff(int r, uint8_t* out, bool mont) {
+        for (int a = 0; a < 2; a++) {
+            int e = ((r & 1) * 3 + (r >> 1)) * 2 + a;
+            if (mont) { for (int i = 0; i < N; i++) ((uint32_t*)out)[e * N + i] = 0; }
+            else { for (int i = 0; i < C::FP_BYTES; i++) out[(11 - e) * C::FP_BYTES + i] = 0; }
+        }
+    }
     B200_HD bool coeff_is_one_part(int r, uint32_t fb) {
         const uint32_t* src = ctx.slots + (fb + r) * SW;
         uint32_t d = 0;
@@ -481,14 +489,14 @@ vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_
     // group-wide view of the zero flags: pair k is dead if P (roles 0,1) or Q (roles 2..5) is all zero
     const unsigned b0 = __ballot_sync(0xffffffffu, z0 != 0), b1 = __ballot_sync(0xffffffffu, z1 != 0);
     const unsigned any_err = __ballot_sync(0xffffffffu, e != 0);
-    if (any_err) {
-        if (lane == 0) atomicExch(err, 1);
-        return;
-    }
     const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+    // a rejected encoding fails ITS item only: the flag is raised, the group runs on with both pairs dead and writes a
+    // defined output (zero element / verdict 0); the other groups of the warp are unaffected
+    const bool bad = active && ((any_err >> sh) & 63u) != 0;
+    if (bad && role == 0) atomicExch(err, 1);
     const unsigned m0 = (b0 >> sh) & 63u, m1 = (b1 >> sh) & 63u;
-    const bool dead0 = ((m0 & 3u) == 3u) || ((m0 & 60u) == 60u);
-    const bool dead1 = NP == 2 ? (((m1 & 3u) == 3u) || ((m1 & 60u) == 60u)) : true;
+    const bool dead0 = bad || ((m0 & 3u) == 3u) || ((m0 & 60u) == 60u);
+    const bool dead1 = NP == 2 ? (bad || ((m1 & 3u) == 3u) || ((m1 & 60u) == 60u)) : true;
     D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
     __syncwarp();
     uint32_t fb = D.template miller<NP>();
@@ -496,9 +504,10 @@ vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_
     if (flags & FLAG_UNITY) {
         const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
+        if (active && role == 0) out[item] = (!bad && ((okm >> sh) & 63u) == 63u) ? 1 : 0;
     } else if (active) {
-        D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        if (bad) D.store_zero_coeff(role, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        else D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
     }
 }
 // standalone driver.Curve.FExp on the VM (same slot file / microcode as the pairing kernel)
@@ -533,20 +542,19 @@ vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* e
     typedef Codec<C> CD;
     int e = 0;
     if (active) D.load_coeff(role, 0, in + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
-    if (__ballot_sync(0xffffffffu, e != 0)) {
-        if (lane == 0) atomicExch(err, 1);
-        return;
-    }
+    const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;      // per item, see vm_pairing_kernel
+    if (bad && role == 0) atomicExch(err, 1);
     __syncwarp();
     uint32_t fb = 0;
     if (flags & FLAG_FEXP) fb = D.final_exp(0);
     if (flags & FLAG_UNITY) {
         const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
-        if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
+        if (active && role == 0) out[item] = (!bad && ((okm >> sh) & 63u) == 63u) ? 1 : 0;
     } else if (active) {
-        D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        if (bad) D.store_zero_coeff(role, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        else D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
     }
 }
 
@@ -590,12 +598,10 @@ vm_lines_kernel(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, u
         }
     }
     const unsigned bz = __ballot_sync(0xffffffffu, z != 0);
-    if (__ballot_sync(0xffffffffu, e != 0)) {
-        if (lane == 0) atomicExch(err, 1);
-        return;
-    }
     const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
-    if (active && role == 0) qinf[item] = (((bz >> sh) & 60u) == 60u) ? 1 : 0;
+    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;
+    if (bad && role == 0) atomicExch(err, 1);        // the upload call reads the flag back and fails
+    if (active && role == 0) qinf[item] = (bad || ((bz >> sh) & 60u) == 60u) ? 1 : 0;
     __syncwarp();
     D.precompute_lines(lines + (active ? item : 0) * (size_t)VmDriver<C>::nlines() * 3 * 2 * N);
 }
@@ -605,7 +611,7 @@ vm_lines_kernel(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, u
 template <class C, int NP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)
 vm_pairing_fixed_kernel(size_t n, const uint8_t* g1a, const uint32_t* qa_idx, const uint8_t* g1b, const uint32_t* qb_idx,
-                        const uint32_t* lines, const uint8_t* qinf, uint8_t* out, uint32_t flags, int* err,
+                        const uint32_t* lines, const uint8_t* qinf, uint32_t n_q, uint8_t* out, uint32_t flags, int* err,
                         const uint32_t* mc_words, const VmDirEntry* mc_dir) {
     extern __shared__ uint32_t smem[];
     constexpr int N = C::N;
@@ -638,15 +644,16 @@ vm_pairing_fixed_kernel(size_t n, const uint8_t* g1a, const uint32_t* qa_idx, co
         if (NP == 2) z1 = D.load_coord(role, 1, g1b + item * CD::g1_size(), nullptr, in_mont, &e);
     }
     const unsigned b0 = __ballot_sync(0xffffffffu, z0 != 0), b1 = __ballot_sync(0xffffffffu, z1 != 0);
-    if (__ballot_sync(0xffffffffu, e != 0)) {
-        if (lane == 0) atomicExch(err, 1);
-        return;
-    }
     const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
     const size_t it = active ? item : 0;
-    const uint32_t ra = qa_idx ? qa_idx[it] : 0u, rb = NP == 2 ? (qb_idx ? qb_idx[it] : 1u) : 0u;
-    const bool dead0 = (((b0 >> sh) & 3u) == 3u) || qinf[ra] != 0;
-    const bool dead1 = NP == 2 ? ((((b1 >> sh) & 3u) == 3u) || qinf[rb] != 0) : true;
+    uint32_t ra = qa_idx ? qa_idx[it] : 0u, rb = NP == 2 ? (qb_idx ? qb_idx[it] : 1u) : 0u;
+    // row indices may come straight from device memory (B200_DEVICE_PTRS): an index outside the table is an error of
+    // its item (flag raised, verdict 0 / zero element), never an address
+    if (ra >= n_q || rb >= n_q) { e = 1; ra = 0; rb = 0; }
+    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;
+    if (bad && role == 0) atomicExch(err, 1);
+    const bool dead0 = bad || (((b0 >> sh) & 3u) == 3u) || qinf[ra] != 0;
+    const bool dead1 = NP == 2 ? (bad || (((b1 >> sh) & 3u) == 3u) || qinf[rb] != 0) : true;
     D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
     __syncwarp();
     const size_t rowsz = (size_t)VmDriver<C>::nlines() * 3 * 2 * N;
@@ -655,9 +662,10 @@ vm_pairing_fixed_kernel(size_t n, const uint8_t* g1a, const uint32_t* qa_idx, co
     if (flags & FLAG_UNITY) {
         const bool ok = active ? D.coeff_is_one_part(role, fb) : true;
         const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        if (active && role == 0) out[item] = (((okm >> sh) & 63u) == 63u) ? 1 : 0;
+        if (active && role == 0) out[item] = (!bad && ((okm >> sh) & 63u) == 63u) ? 1 : 0;
     } else if (active) {
-        D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        if (bad) D.store_zero_coeff(role, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        else D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
     }
 }
 
@@ -698,10 +706,9 @@ vm_gt_kernel(int opk, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out
         D.load_coeff(role, 0, a + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
         if (opk == GT_OP_MUL) D.load_coeff(role, 6, b + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
     }
-    if (__ballot_sync(0xffffffffu, e != 0)) {
-        if (lane == 0) atomicExch(err, 1);
-        return;
-    }
+    const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
+    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;      // per item, see vm_pairing_kernel
+    if (bad && role == 0) atomicExch(err, 1);
     __syncwarp();
     uint32_t fb = 12;
     if (opk == GT_OP_MUL) D.run(VP_F12_MUL, 12, 0, 6);
@@ -712,7 +719,10 @@ vm_gt_kernel(int opk, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out
         const int top = __reduce_max_sync(0xffffffffu, len);
         fb = D.gt_exp(k, top);
     }
-    if (active) D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+    if (active) {
+        if (bad) D.store_zero_coeff(role, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        else D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+    }
 }
 #endif
 

@@ -285,7 +285,10 @@ point_codec_kernel(int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t f
     constexpr size_t FB = C::FP_BYTES;
     const size_t usz = (G2 ? 4 : 2) * FB, csz = (G2 ? 2 : 1) * FB;
     const size_t isz = op == 0 ? csz : usz, osz = op == 0 ? usz : (op == 1 ? csz : 1);
-    if (point_codec_item<C, G2>(op, in + i * isz, out + i * osz, flags)) atomicExch(err, 1);
+    if (point_codec_item<C, G2>(op, in + i * isz, out + i * osz, flags)) {
+        atomicExch(err, 1);
+        for (size_t b = 0; b < osz; b++) out[i * osz + b] = 0;          // defined output for the rejected item
+    }
 }
 #endif
 

@@ -39,3 +39,28 @@ def msm_sharded(curve, pts, scalars, n, dist, device=None, msm_fn=None, sum_fn=N
     partial = msm_fn(pts[lo * g1sz:hi * g1sz], scalars[lo * 32:hi * 32], hi - lo)
     parts = gather_bytes(partial, dist, device)
     return sum_fn(parts)
+
+
+def msm_sharded_device(lib, cid, d_pts, d_scalars, n_local, dist, device, in_flags=0, out_flags=0, scratch=None):
+    """Device-resident flavour: this rank's point range (torch uint8 tensor on `device`, BYTES or MONT per in_flags) and
+    scalars stay in HBM; local MSM -> 2*FpBytes affine partial (Montgomery limbs) -> NCCL all-gather -> b200_g1_sum.
+    Everything is enqueued on the current stream; returns the device tensor holding the combined point (every rank has
+    it).  `scratch` = (partial, gathered, out) tensors to reuse between calls."""
+    import torch
+    from ._lib import DEVICE_PTRS, IN_MONT, OUT_MONT, check
+    world = dist.get_world_size() if dist is not None else 1
+    g1sz = 2 * lib.b200_fp_bytes(cid)
+    if scratch is None:
+        scratch = (torch.empty(g1sz, dtype=torch.uint8, device=device),
+                   torch.empty(world * g1sz, dtype=torch.uint8, device=device),
+                   torch.empty(g1sz, dtype=torch.uint8, device=device))
+    part, gath, out = scratch
+    check(lib.b200_g1_msm(cid, n_local, d_pts.data_ptr() if n_local else None, d_scalars.data_ptr() if n_local else None,
+                          part.data_ptr(), DEVICE_PTRS | in_flags | OUT_MONT))
+    if world > 1:
+        dist.all_gather_into_tensor(gath, part)
+        src = gath
+    else:
+        src = part
+    check(lib.b200_g1_sum(cid, world, src.data_ptr(), out.data_ptr(), DEVICE_PTRS | IN_MONT | out_flags))
+    return out

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-budget", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-budget", "1", "--no-extra"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout
@@ -23,6 +23,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # same workload description as the GPU arm (the driver compares the two config objects)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.headline_config(bench.BATCH, 1)
+    assert d["cpu_baseline"]["per_thread"] * d["cpu_baseline"]["cores"] == d["value"]
 
 
 def test_reference_arm_other_ranks_are_silent():

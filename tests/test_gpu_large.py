@@ -23,7 +23,7 @@ def rand_inputs(m, cid, n, seed):
     return bench.make_inputs(m, cid, n, seed=seed)
 
 
-@pytest.mark.parametrize("cid", [1, 3, 4, 5])
+@pytest.mark.parametrize("cid", [1, 3, 4, 5, 6, 7])
 def test_pairing2_random_vs_cpu_oracle(m, cid):
     """1,000 random Pairing2 (+FExp) per curve id, raw and exponentiated bytes, against oracle/cpu."""
     from oracle import cpu_binding as orc
@@ -43,7 +43,7 @@ def test_pairing2_random_vs_cpu_oracle(m, cid):
     assert raw1 == orc.pairing_batch(cid, n, g1a, g2a)
 
 
-@pytest.mark.parametrize("cid", [1, 4, 5])
+@pytest.mark.parametrize("cid", [1, 4, 5, 6])
 def test_g1_mul_random_vs_cpu_oracle(m, cid):
     from oracle import cpu_binding as orc
     c = m.Curves[cid]
@@ -130,6 +130,43 @@ def test_full_size_properties(m):
     b = c5.NewG1FromBytes(c5.MsmBatch(pts, k2.tobytes(), nm))
     a.Add(b)
     assert a.Bytes() == c5.MsmBatch(pts, ksum.tobytes(), nm)
+
+
+def _points_on_gpu(m, cid, n, seed):
+    """n distinct G1 points [k_i]G in Bytes() form, made by the GPU (b200_g1_mul_batch is itself oracle-checked above)."""
+    import bench
+    c = m.Curves[cid]
+    ks = bench.scalars_mod_r(np.random.default_rng(seed), n, cid)
+    return b"".join(p.Bytes() for p in c.G1MulBatch(c.GenG1.Bytes() * n, ks.tobytes(), n))
+
+
+@pytest.mark.parametrize("cid,lg", [(5, 20), (4, 21)])
+def test_msm_baseline_sizes_vs_cpu_oracle(m, cid, lg):
+    """BASELINE configs[2] / one GPU's share of configs[3]: 2^20 BLS12-381 and 2^21 BLS12-377 points, scalars uniform in
+    [0, r), against the CPU oracle's Pippenger (reference call site bls12381/bls12-381.go:766-783)."""
+    import bench
+    from oracle import cpu_binding as orc
+    c = m.Curves[cid]
+    n = 1 << lg
+    nd = 1 << 16                                   # distinct points, tiled (the bucket sums see every point 2^(lg-16) times)
+    pts = _points_on_gpu(m, cid, nd, 40 + cid) * (n // nd)
+    ks = bench.scalars_mod_r(np.random.default_rng(50 + cid), n, cid).tobytes()
+    assert c.MsmBatch(pts, ks, n) == orc.g1_msm(cid, n, pts, ks)
+
+
+def test_bn254_65536_pairing_fexp_sampled_vs_cpu_oracle(m):
+    """BASELINE configs[1]: 65,536 BN254 Pairing+FExp on the GPU, every 32nd result (2,048 samples) compared byte for byte
+    with the CPU oracle; the raw Miller bytes of the same samples too."""
+    from oracle import cpu_binding as orc
+    c = m.Curves[1]
+    n, stride = 65536, 32
+    g1a, g2a, _, _, _ = rand_inputs(m, 1, n, seed=31)
+    out = c.PairingBatch(g1a, g2a, n, m.FEXP)
+    gs, qs, ts = c.G1ByteSize, c.G2ByteSize, c.GtByteSize
+    idx = range(0, n, stride)
+    s1 = b"".join(g1a[i * gs:(i + 1) * gs] for i in idx)
+    s2 = b"".join(g2a[i * qs:(i + 1) * qs] for i in idx)
+    assert b"".join(out[i * ts:(i + 1) * ts] for i in idx) == orc.pairing_batch(1, len(idx), s1, s2, fexp=True)
 
 
 def test_multi_gpu_split_matches_single(m):
@@ -305,3 +342,20 @@ def test_fixed_q_pairings_match_general_path(m, cid):
     c.G2LinesFree(h2)
     with pytest.raises(m.B200Error):
         c.Pairing2FixedBatch(h2, A, None, B, None, 64, m.FEXP)
+
+
+def test_torchrun_two_ranks_sharded_msm(m):
+    """SURVEY 8e line 2 on hardware: two processes, one GPU each, range-split MSM + NCCL all-gather of the partial sums
+    + b200_g1_sum (mathlib_b200.shard.msm_sharded_device), checked against the CPU oracle inside the worker."""
+    import subprocess
+    import sys
+    lib = m.load()
+    if lib.b200_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(HERE)
+    port = 29600 + os.getpid() % 300
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(HERE, "dist_msm_worker.py")], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "SHARDED_MSM_OK ranks=2" in out.stdout

@@ -12,11 +12,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CURVE_IDS = [1, 3, 4, 5]
+CURVE_IDS = [1, 3, 4, 5, 6, 7]
+# the BBS curve ids differ from 3 / 5 only in HashToG1 (reference math.go:219-255): same arithmetic, same vectors
+VECTOR_FILE = {1: 1, 3: 3, 4: 4, 5: 5, 6: 3, 7: 5}
 
 
 def load_vectors(cid):
-    with open(os.path.join(HERE, "golden", "vectors_%d.json" % cid)) as f:
+    with open(os.path.join(HERE, "golden", "vectors_%d.json" % VECTOR_FILE[cid])) as f:
         return json.load(f)
 
 
@@ -137,6 +139,75 @@ def test_bad_encoding_is_an_error(m):
         c.G1MulBatch(bad, (1).to_bytes(32, "big"), 1)
     with pytest.raises(m.B200Error):
         m.check(m.load().b200_fp_bytes(99))
+
+
+def test_device_ptrs_rejected_item_is_per_item(m):
+    """B200_DEVICE_PTRS calls cannot return B200_ERR_ENCODING (they are asynchronous): a rejected item gets a defined
+    output -- verdict 0 / all-zero element, never a stale 'pass' -- its neighbours in the warp are computed normally, and
+    b200_take_error reports and clears the flag.  Same for a fixed-Q row index outside the table."""
+    import ctypes
+    import numpy as np
+    import torch
+    import bench
+    lib = m.load()
+    c = m.Curves[3]
+    n = 12
+    g1a, g2a, g1b, g2b, expect = bench.make_inputs(m, 3, n, seed=5)
+    good = c.Pairing2Batch(g1a, g2a, g1b, g2b, n, m.FEXP)
+    bad_i = 4
+    gs, ts = c.G1ByteSize, c.GtByteSize
+    g1a_bad = g1a[:bad_i * gs] + b"\x1f" + b"\xff" * (gs - 1) + g1a[(bad_i + 1) * gs:]          # x >= p
+    with pytest.raises(m.B200Error):                                                             # host buffers: the call fails
+        c.Pairing2Batch(g1a_bad, g2a, g1b, g2b, n, m.FEXP)
+    dev = torch.device("cuda", 0)
+    m.check(lib.b200_set_device(0))
+    m.check(lib.b200_set_stream(torch.cuda.current_stream().cuda_stream))
+    d = [torch.frombuffer(bytearray(x), dtype=torch.uint8).to(dev) for x in (g1a_bad, g2a, g1b, g2b)]
+    had = ctypes.c_int(7)
+    m.check(lib.b200_take_error(ctypes.byref(had)))                                              # clear earlier state
+    ver = torch.ones(n, dtype=torch.uint8, device=dev)                                           # stale "pass" everywhere
+    m.check(lib.b200_pairing2_batch(3, n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                                    ver.data_ptr(), m.DEVICE_PTRS | m.FEXP | m.OUT_UNITY_ONLY))
+    m.check(lib.b200_take_error(ctypes.byref(had)))
+    assert had.value == 1
+    want = np.array(expect, dtype=np.uint8)
+    want[bad_i] = 0
+    assert (ver.cpu().numpy() == want).all()
+    m.check(lib.b200_take_error(ctypes.byref(had)))
+    assert had.value == 0                                                                        # taking clears it
+    out = torch.full((n * ts,), 0xAB, dtype=torch.uint8, device=dev)
+    m.check(lib.b200_pairing2_batch(3, n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                                    out.data_ptr(), m.DEVICE_PTRS | m.FEXP))
+    m.check(lib.b200_take_error(ctypes.byref(had)))
+    got = out.cpu().numpy().tobytes()
+    assert had.value == 1 and got[bad_i * ts:(bad_i + 1) * ts] == bytes(ts)
+    assert got[:bad_i * ts] == good[:bad_i * ts] and got[(bad_i + 1) * ts:] == good[(bad_i + 1) * ts:]
+    # G1.Mul with a bad point: zero output for that item only
+    ks = torch.frombuffer(bytearray((5).to_bytes(32, "big") * n), dtype=torch.uint8).to(dev)
+    o1 = torch.full((n * gs,), 0xAB, dtype=torch.uint8, device=dev)
+    m.check(lib.b200_g1_mul_batch(3, n, d[0].data_ptr(), ks.data_ptr(), o1.data_ptr(), m.DEVICE_PTRS))
+    m.check(lib.b200_take_error(ctypes.byref(had)))
+    g = o1.cpu().numpy().tobytes()
+    ref = b"".join(p.Bytes() for p in c.G1MulBatch(g1a, (5).to_bytes(32, "big") * n, n))
+    assert had.value == 1 and g[bad_i * gs:(bad_i + 1) * gs] == bytes(gs)
+    assert g[:bad_i * gs] == ref[:bad_i * gs] and g[(bad_i + 1) * gs:] == ref[(bad_i + 1) * gs:]
+    # fixed-Q: a device-side row index outside the table must not become an address
+    h = c.G2LinesUpload(g2a[:c.G2ByteSize] + c.GenG2.Bytes(), 2)
+    rows_a = np.zeros(n, dtype=np.uint32)
+    rows_b = np.ones(n, dtype=np.uint32)
+    rows_b[7] = 1 << 30
+    da, db = torch.from_numpy(rows_a.view(np.int32)).to(dev), torch.from_numpy(rows_b.view(np.int32)).to(dev)
+    dg = torch.frombuffer(bytearray(g1a), dtype=torch.uint8).to(dev)
+    ver = torch.ones(n, dtype=torch.uint8, device=dev)
+    m.check(lib.b200_pairing2_fixed_batch(h, n, dg.data_ptr(), da.data_ptr(), d[2].data_ptr(), db.data_ptr(), ver.data_ptr(),
+                                          m.DEVICE_PTRS | m.FEXP | m.OUT_UNITY_ONLY))
+    m.check(lib.b200_take_error(ctypes.byref(had)))
+    v = ver.cpu().numpy()
+    assert had.value == 1 and v[7] == 0
+    ok = c.Pairing2FixedBatch(h, g1a, [0] * n, g1b, [1] * n, n, m.FEXP | m.OUT_UNITY_ONLY)
+    assert all(v[i] == ok[i] for i in range(n) if i != 7)
+    c.G2LinesFree(h)
+    m.check(lib.b200_set_stream(None))
 
 
 # ---- SURVEY 8(f) row 3: the callers next to the hot path -------------------------------------------------------------

@@ -177,6 +177,13 @@ def cpu_reference_rate(cid, inputs, n_sample, budget_s, nthreads=0):
 
 
 _REAL_STDOUT = None
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (the JSON line is the only thing on stdout)"""
+    sys.stderr.write("[bench %6.1fs rank %s] %s\n" % (time.time() - _T0, os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
 
 
 def quiet_stdout():
@@ -332,6 +339,7 @@ def main():
     warmup = max(3, args.warmup)
 
     # ---- inputs (each rank its own batch: weak scaling, no data-path collective)
+    log("library loaded, making %d checks" % n)
     g1a, g2a, g1b, g2b, expect = make_inputs(m, CID, n, seed=1 + rank)
     host = [torch.frombuffer(bytearray(x), dtype=torch.uint8).pin_memory() for x in (g1a, g2a, g1b, g2b)]
     d_in = [h.to(dev) for h in host]
@@ -354,6 +362,7 @@ def main():
         torch.cuda.synchronize()
 
     # correctness of the timed path before timing it: valid checks are 1, random ones are not
+    log("inputs ready, first launch")
     step_device()
     torch.cuda.synchronize()
     got = d_out.cpu().numpy().reshape(n, c.GtByteSize)
@@ -362,6 +371,7 @@ def main():
     if not (is_one == expect).all():
         raise SystemExit("bench: Pairing2+FExp verdicts are wrong -- refusing to time a broken kernel")
 
+    log("verdicts ok, timing")
     for _ in range(warmup):
         step_device()
     barrier()
@@ -382,6 +392,7 @@ def main():
     clocks = sampler.stop()
 
     # ---- e2e through the C ABI with host buffers
+    log("device-resident: %.2f ms per step; e2e" % (dev_ms / args.steps))
     for _ in range(2):
         step_e2e()
     barrier()
@@ -403,6 +414,7 @@ def main():
 
     # ---- the BASELINE configs, at every N (collective ops inside: every rank takes part)
     extra = {}
+    log("e2e %.2f ms per step; BASELINE configs" % (e2e_ms / args.steps))
     if not args.no_extra:
         try:
             extra = run_configs(m, lib, dev, stream, torch, dist, rank, world, args)
@@ -454,6 +466,7 @@ def main():
     }
 
     # ---- CPU baseline (oracle/cpu port, all host threads, bounded sample)
+    log("CPU baseline")
     cpu = None
     try:
         rate, nt, done, dt = cpu_reference_rate(CID, (g1a, g2a, g1b, g2b), 256, args.cpu_budget)
@@ -532,6 +545,7 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
     from mathlib_b200 import shard
 
     # ---------------------------------------------------------------------------------------------- configs[0]
+    log("configs[0]")
     # exactly 1,024 BLS12_381 (kilic) Pairing2+FExp checks per GPU
     c = m.Curves[3]
     n0 = 1024
@@ -557,6 +571,7 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
     del d, o
 
     # ---------------------------------------------------------------------------------------------- configs[1]
+    log("configs[1]")
     if world == 1:
         c = m.Curves[1]
         n1 = 65536
@@ -572,6 +587,7 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
         del d, o
 
     # ---------------------------------------------------------------------------------------------- configs[2]
+    log("configs[2]")
     # BLS12_381_GURVY G1 MultiScalarMul, 2^20 points / scalars uniform in [0, r), STRONG-scaled: rank k owns the point
     # range [n k / N, n (k+1) / N); one affine partial sum per rank, 96-byte all-gather, b200_g1_sum.
     cid = 5
@@ -681,6 +697,7 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
     del gen, d_kp, pts_bytes, pts_mont, d_k, h_pts
 
     # ---------------------------------------------------------------------------------------------- configs[3]
+    log("configs[3]")
     # BLS12_377_GURVY MSM, 2^21 points per rank (2^24 over 8 GPUs) + partial-sum combine: WEAK scaling
     cid = 4
     c = m.Curves[cid]
@@ -732,6 +749,7 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
     del gen, pts, d_kp, d_k
 
     # ---------------------------------------------------------------------------------------------- configs[4]
+    log("configs[4]")
     # BLS12_381_BBS: 12,500 BBS-style verifications per rank (100k at 8 GPUs) = Mul2 (B = [e]G1 + [f]A) feeding
     # Pairing2+FExp -> IsUnity on the device, G2 arguments fixed (public key, generator); every second one is valid
     import random

@@ -163,6 +163,17 @@ int b200_g2_compress_batch(int curve, size_t n, const void* pts, void* compresse
 int b200_g1_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 int b200_g2_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 
+/* ---- hash-to-G1 for whole batches: driver.Curve.HashToG1 / HashToG1WithDomain
+   (reference driver/math.go:120-131).  BLS12-381 curve ids only:
+     3, 5  kilic g1.HashToCurve / gnark bls12381.HashToG1 (reference driver/kilic/bls12-381.go:410-447,
+           driver/gurvy/bls12381/bls12-381.go:652-677) = RFC 9380 BLS12381G1_XMD:SHA-256_SSWU_RO_ with `domain` as DST;
+     6, 7  the BBS variant HashToG1GenericBESwu (reference driver/kilic/custom.go:205-237, driver/gurvy/custom.go:152-193):
+           BLAKE2b-512 in expand_message_xmd and the big-endian sign rule.
+   Message i is msgs[offsets[i] .. offsets[i+1]) (n + 1 offsets); one domain (<= 255 bytes, may be empty) for the batch.
+   out: n affine G1 elements (BYTES, or MONT limbs with B200_OUT_MONT).  Other curve ids fail with B200_ERR_ARG. */
+int b200_hash_to_g1_batch(int curve, size_t n, const void* msgs, const uint64_t* offsets, const void* domain,
+                          size_t domain_len, void* out, uint32_t flags);
+
 /* Number of kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
 uint64_t b200_launch_count(void);
 

@@ -807,6 +807,50 @@ int b200_g2_validate_batch(int curve, size_t n, const void* in, void* ok_out, ui
     return point_codec_batch(curve, 1, 2, n, in, ok_out, flags);
 }
 
+int b200_hash_to_g1_batch(int curve, size_t n, const void* msgs, const uint64_t* offsets, const void* domain,
+                          size_t domain_len, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    const CurveVTable* vt = ci.vt;
+    if (!vt->hash_to_g1 || curve == B200_BLS12_377_GURVY)
+        return fail(B200_ERR_ARG, "HashToG1 is built for the BLS12-381 curve ids (3, 5, 6, 7) only");
+    if (domain_len > 255) return fail(B200_ERR_ARG, "invalid domain length");          // same refusal as custom.go:260-262
+    if (n == 0) return 0;
+    if (!offsets || !out || (domain_len && !domain)) return fail(B200_ERR_ARG, "null buffer");
+    const int bbs = (curve == B200_BLS12_381_BBS || curve == B200_BLS12_381_BBS_GURVY) ? 1 : 0;
+    const uint32_t kf = kernel_flags(flags) & B200_OUT_MONT;
+    int dev = current_device();
+    CU(cudaSetDevice(dev));
+    if (flags & B200_DEVICE_PTRS) {
+        CU(vt->hash_to_g1(bbs, n, (const uint8_t*)msgs, offsets, (const uint8_t*)domain, domain_len, (uint8_t*)out, kf, t_stream));
+        return 0;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(B200_ERR_ARG, "message offsets must be non-decreasing");
+    const size_t total = (size_t)(offsets[n] - offsets[0]);
+    if (total && !msgs) return fail(B200_ERR_ARG, "null buffer");
+    WsGuard g(dev);
+    if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
+    Workspace& w = *g.w;
+    const size_t osz = n * 2 * (size_t)vt->fp_bytes;
+    if (int rc = w.reserve(align_up(total + 1) + align_up((n + 1) * 8) + align_up(domain_len + 1) + align_up(osz))) return rc;
+    uint8_t* d_msg = w.buf;
+    uint64_t* d_off = (uint64_t*)(d_msg + align_up(total + 1));
+    uint8_t* d_dst = (uint8_t*)d_off + align_up((n + 1) * 8);
+    uint8_t* d_out = d_dst + align_up(domain_len + 1);
+    // offsets are rebased to the staged copy, which starts at the first message
+    std::vector<uint64_t> rel(n + 1);
+    for (size_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+    if (total) CU(cudaMemcpyAsync(d_msg, (const uint8_t*)msgs + offsets[0], total, cudaMemcpyHostToDevice, w.stream));
+    CU(cudaMemcpyAsync(d_off, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, w.stream));
+    if (domain_len) CU(cudaMemcpyAsync(d_dst, domain, domain_len, cudaMemcpyHostToDevice, w.stream));
+    CU(vt->hash_to_g1(bbs, n, d_msg, d_off, d_dst, domain_len, d_out, kf, w.stream));
+    CU(cudaMemcpyAsync(out, d_out, osz, cudaMemcpyDeviceToHost, w.stream));
+    CU(cudaStreamSynchronize(w.stream));
+    return 0;
+}
+
 int b200_gt_mul_batch(int curve, size_t n, const void* a, const void* b, void* out, uint32_t flags) {
     return elementwise_batch(curve, n, {{a, 12, nullptr}, {b, 12, nullptr}}, out, 12, flags, 256,
                              [](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out, uint32_t kf,

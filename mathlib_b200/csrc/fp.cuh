@@ -338,9 +338,13 @@ struct FpOps {
         B[N] = addc(B[N], 0);
     }
 
-    // out-of-line product for callers whose hot loop must stay inside the instruction cache (G1 point formulas)
-    static B200_HD_NOINLINE void mulx(E& r, const E& a, const E& b) { mul(r, a, b); }
-    static B200_HD void sqrx(E& r, const E& a) { mulx(r, a, a); }
+    // out-of-line product for callers whose hot loop must stay inside the instruction cache (G1 point formulas).
+    // Operands and result travel BY VALUE: the device ABI passes them in registers (24 words in, 12 out), whereas
+    // references would force every operand through a local-memory stack slot -- with ~200 KB of shared memory per SM the
+    // L1 is nearly gone and that traffic went to L2 / DRAM (round 1: 39 GB written by one 2^21-point g1_mul launch).
+    static B200_HD_NOINLINE E mulv(E a, E b) { E r; mul(r, a, b); return r; }
+    static B200_HD void mulx(E& r, const E& a, const E& b) { r = mulv(a, b); }
+    static B200_HD void sqrx(E& r, const E& a) { r = mulv(a, a); }
 
     // Montgomery form conversions
     static B200_HD void to_mont(E& r, const E& a) {

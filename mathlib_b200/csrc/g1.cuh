@@ -35,7 +35,7 @@ struct G1Ops {
     static B200_HD void neg(Pt& r, const Pt& a) { r.x = a.x; F::neg(r.y, a.y); r.zz = a.zz; r.zzz = a.zzz; }
 
     // p <- 2a for affine a (mdbl-2008-s-1)
-    static B200_HD_NOINLINE void dbl_affine(Pt& p, const Aff& a) {
+    static B200_HD void dbl_affine(Pt& p, const Aff& a) {
         if (aff_is_inf(a) || F::is_zero(a.y)) { set_inf(p); return; }
         E U, V, W, S, M, t;
         F::dbl(U, a.y);
@@ -54,7 +54,7 @@ struct G1Ops {
         p.zzz = W;
     }
     // p <- 2p (dbl-2008-s-1)
-    static B200_HD_NOINLINE void dbl(Pt& p) {
+    static B200_HD void dbl(Pt& p) {
         if (is_inf(p)) return;
         E U, V, W, S, M, t;
         F::dbl(U, p.y);
@@ -73,7 +73,7 @@ struct G1Ops {
         F::mulx(p.zzz, W, p.zzz);
     }
     // p <- p + a, a affine (madd-2008-s), complete
-    static B200_HD_NOINLINE void madd(Pt& p, const Aff& a) {
+    static B200_HD void madd(Pt& p, const Aff& a) {
         if (aff_is_inf(a)) return;
         if (is_inf(p)) { from_affine(p, a); return; }
         E U2, S2, Pp, R, PP, PPP, Q, t;
@@ -99,7 +99,7 @@ struct G1Ops {
         F::mulx(p.zzz, p.zzz, PPP);
     }
     // p <- p + q (add-2008-s), complete
-    static B200_HD_NOINLINE void add(Pt& p, const Pt& q) {
+    static B200_HD void add(Pt& p, const Pt& q) {
         if (is_inf(q)) return;
         if (is_inf(p)) { p = q; return; }
         E U1, U2, S1, S2, Pp, R, PP, PPP, Q, t;
@@ -195,7 +195,7 @@ struct G1Ops {
         F::neg(t.x3, t.x3);
         F::neg(t.ny, base.y);
     }
-    static B200_HD_NOINLINE void glv_step(Pt& acc, const GlvTable& t, uint32_t b) {    // b in 1..3
+    static B200_HD void glv_step(Pt& acc, const GlvTable& t, uint32_t b) {    // b in 1..3
         Aff s;
         s.x = b == 1 ? t.x1 : (b == 2 ? t.x2 : t.x3);
         s.y = b == 3 ? t.ny : t.y;

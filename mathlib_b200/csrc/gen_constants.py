@@ -100,6 +100,91 @@ def tonelli(a, p):
     return rr
 
 
+def h2c_bls381(p, r, x):
+    """Constants of BLS12-381 hash-to-G1 (hash_to_g1.cuh): the simplified-SWU parameters of the 11-isogenous curve
+    E': y^2 = x^3 + A x + B (the values the reference holds at driver/kilic/custom.go:26-42) and the 11-isogeny E' -> E,
+    DERIVED here with Velu's formulas: E'(Fp) has one rational subgroup of order 11, its quotient is y^2 = x^3 + 4 * 11^6,
+    and (x, y) -> (x / 11^2, y / 11^3) lands on E.  tests/test_hash_to_g1.py checks the resulting map against RFC 9380's
+    known answers.  Returns (A, B, Z, xnum, xden, ynum, yden) with coefficient lists low degree first (dens monic)."""
+    A = 0x144698a3b8e9433d693a02c96d4982b0ea985383ee66a8d8e8981aefd881ac98936f8da0e0f97f5cf428082d584c1d
+    B = 0x12e2908d11688030018b12e8753eee3b2016c1f0f24f4070a0b9c14fcef35ef55a23215a316ceaa5d1cc48e98e172be0
+
+    def add(P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        if P[0] == Q[0]:
+            if (P[1] + Q[1]) % p == 0:
+                return None
+            m = (3 * P[0] * P[0] + A) * pow(2 * P[1], -1, p) % p
+        else:
+            m = (Q[1] - P[1]) * pow(Q[0] - P[0], -1, p) % p
+        x3 = (m * m - P[0] - Q[0]) % p
+        return (x3, (m * (P[0] - x3) - P[1]) % p)
+
+    def mul(P, k):
+        R_ = None
+        while k:
+            if k & 1:
+                R_ = add(R_, P)
+            P = add(P, P)
+            k >>= 1
+        return R_
+
+    def pmul(a, b):
+        o = [0] * (len(a) + len(b) - 1)
+        for i, u in enumerate(a):
+            for j, v in enumerate(b):
+                o[i + j] = (o[i + j] + u * v) % p
+        return o
+
+    def padd(a, b):
+        n = max(len(a), len(b))
+        return [((a[i] if i < len(a) else 0) + (b[i] if i < len(b) else 0)) % p for i in range(n)]
+
+    def pder(a):
+        return [a[i] * i % p for i in range(1, len(a))]
+
+    cof = (x - 1) ** 2 // 3 * r // 121
+    xx = 0
+    while True:
+        xx += 1
+        rhs = (xx ** 3 + A * xx + B) % p
+        y = pow(rhs, (p + 1) // 4, p)
+        if y * y % p != rhs:
+            continue
+        Q = mul((xx, y), cof)
+        if Q is None:
+            continue
+        if mul(Q, 11) is not None:
+            Q = mul(Q, 11)
+        break
+    assert mul(Q, 11) is None
+    terms, h, v, w = [], [1], 0, 0
+    for i in range(1, 6):
+        xi, yi = mul(Q, i)
+        vi, ui = 2 * (3 * xi * xi + A) % p, 4 * yi * yi % p
+        v, w = (v + vi) % p, (w + ui + xi * vi) % p
+        terms.append((xi, vi, ui))
+        h = pmul(h, [(-xi) % p, 1])
+    assert (A - 5 * v) % p == 0 and (B - 7 * w) % p == 4 * 11 ** 6
+    h2 = pmul(h, h)
+    N = pmul([0, 1], h2)
+    for xi, vi, ui in terms:
+        others = [1]
+        for xj, _, _ in terms:
+            if xj != xi:
+                others = pmul(others, [(-xj) % p, 1])
+        o2 = pmul(others, others)
+        N = padd(N, [c * vi % p for c in pmul([(-xi) % p, 1], o2)])
+        N = padd(N, [c * ui % p for c in o2])
+    Yn = padd(pmul(pder(N), h), [c * (p - 2) % p for c in pmul(N, pder(h))])
+    h3 = pmul(h2, h)
+    i2, i3 = pow(121, -1, p), pow(1331, -1, p)
+    return A, B, 11, [c * i2 % p for c in N], h2, [c * i3 % p for c in Yn], h3
+
+
 def limbs(v, n):
     return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
 
@@ -190,6 +275,20 @@ def main():
         out.append('#define %s_TS_EXP %s' % (name, fmt(limbs((q_ - 1) // 2, n))))
         out.append('#define %s_TS_Z %s' % (name, fmt(mont(pow(g_, q_, p)))))
         out.append('#define %s_HALF_P %s' % (name, fmt(limbs((p - 1) // 2, n))))
+        if name == 'BLS381':
+            hA, hB, hZ, xnum, xden, ynum, yden = h2c_bls381(p, r, c['x'])
+            assert len(xnum) == 12 and len(xden) == 11 and len(ynum) == 16 and len(yden) == 16 and xden[-1] == 1 and yden[-1] == 1
+            out.append('#define BLS381_H2C_A %s' % fmt(mont(hA)))
+            out.append('#define BLS381_H2C_B %s' % fmt(mont(hB)))
+            out.append('#define BLS381_H2C_MBA %s' % fmt(mont(-hB * pow(hA, -1, p) % p)))
+            out.append('#define BLS381_H2C_X1EXC %s' % fmt(mont(hB * pow(hZ * hA, -1, p) % p)))
+            out.append('#define BLS381_H2C_Z %s' % fmt(mont(hZ)))
+            out.append('#define BLS381_H2C_CF %s' % fmt(limbs((1 << 256) * R * R % p, n)))
+            for nm, cs in (('XNUM', xnum), ('XDEN', xden[:-1]), ('YNUM', ynum), ('YDEN', yden[:-1])):
+                vals = []
+                for cc in cs:
+                    vals += mont(cc)
+                out.append('#define BLS381_H2C_%s %s' % (nm, fmt(vals)))
         # Frobenius: gamma[k][i] = xi^(i*(p^k-1)/6), k=1..3, i=1..5
         for k in (1, 2, 3):
             e = (p ** k - 1) // 6

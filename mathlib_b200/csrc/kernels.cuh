@@ -194,7 +194,7 @@ fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err)
 
 #define B200_G1_THREADS 128
 #ifndef B200_G1_MIN_BLOCKS
-#define B200_G1_MIN_BLOCKS 4        // 16 warps per SM: caps the kernels at 128 registers (measured against 2 blocks at 186)
+#define B200_G1_MIN_BLOCKS 3        // 12 warps per SM at <= 168 registers: the accumulator point and the formula temporaries stay in registers
 #endif
 
 template <class C>

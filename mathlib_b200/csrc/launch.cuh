@@ -12,6 +12,7 @@
 #include "g2.cuh"
 #include "points.cuh"
 #include "g1_p3.cuh"
+#include "hash_to_g1.cuh"
 
 namespace b200 {
 
@@ -65,6 +66,9 @@ struct CurveVTable {
     // point decompression (op 0) / compression (1) / validation (2) batches, g2 = 0 / 1
     cudaError_t (*point_codec)(int g2, int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err,
                                cudaStream_t s);
+    // hash-to-G1 batch (BLS12-381 only; nullptr on the other curves)
+    cudaError_t (*hash_to_g1)(int bbs, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst, size_t dlen,
+                              uint8_t* out, uint32_t flags, cudaStream_t s);
     // points -> Montgomery affine array (for MSM / resident bases)
     cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
     // resident window tables: tab[w*stride + i] = 2^(c*w) * tab[i]
@@ -299,6 +303,13 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
+    static cudaError_t hash_to_g1(int bbs, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst,
+                                  size_t dlen, uint8_t* out, uint32_t flags, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        hash_to_g1_kernel<<<blocks_for(n, 64), 64, 0, s>>>(bbs, n, msgs, offsets, dst, dlen, out, flags);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
     static cudaError_t g2_mul(size_t n, const uint8_t* pts, const uint8_t* k, uint8_t* out, uint32_t flags, int* err,
                               cudaStream_t s) {
         if (n == 0) return cudaSuccess;
@@ -431,7 +442,8 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
-                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec, &msm_points, &msm_tables, &msm};
+                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec,
+                                      (C::N == 12 && C::BETA == -1) ? &hash_to_g1 : nullptr, &msm_points, &msm_tables, &msm};
         return &t;
     }
 };

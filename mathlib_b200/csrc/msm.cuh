@@ -268,8 +268,11 @@ msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const Ms
     buckets[it.bucket] = acc;
 }
 
+#ifndef B200_MSM_ACC_MIN_BLOCKS
+#define B200_MSM_ACC_MIN_BLOCKS 4      // measured at 2^20 points: 2 blocks (188 regs) 9.64 ms, 3 (168) 9.25 ms, 4 (128, a few spills) 9.17 ms
+#endif
 template <class C>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, B200_MSM_ACC_MIN_BLOCKS)
 msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
                       const uint32_t* sorted, const uint32_t* perm, G1XYZZ<C::N>* buckets) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -543,7 +543,8 @@ vm_fexp_kernel(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* e
     int e = 0;
     if (active) D.load_coeff(role, 0, in + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
     const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
-    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;      // per item, see vm_pairing_kernel
+    const unsigned errm = __ballot_sync(0xffffffffu, e != 0);      // every lane votes: no short-circuit around it
+    const bool bad = active && ((errm >> sh) & 63u) != 0;      // per item, see vm_pairing_kernel
     if (bad && role == 0) atomicExch(err, 1);
     __syncwarp();
     uint32_t fb = 0;
@@ -599,7 +600,8 @@ vm_lines_kernel(size_t n_q, const uint8_t* g2, uint32_t* lines, uint8_t* qinf, u
     }
     const unsigned bz = __ballot_sync(0xffffffffu, z != 0);
     const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
-    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;
+    const unsigned errm = __ballot_sync(0xffffffffu, e != 0);      // every lane votes: no short-circuit around it
+    const bool bad = active && ((errm >> sh) & 63u) != 0;
     if (bad && role == 0) atomicExch(err, 1);        // the upload call reads the flag back and fails
     if (active && role == 0) qinf[item] = (bad || ((bz >> sh) & 60u) == 60u) ? 1 : 0;
     __syncwarp();
@@ -650,7 +652,8 @@ vm_pairing_fixed_kernel(size_t n, const uint8_t* g1a, const uint32_t* qa_idx, co
     // row indices may come straight from device memory (B200_DEVICE_PTRS): an index outside the table is an error of
     // its item (flag raised, verdict 0 / zero element), never an address
     if (ra >= n_q || rb >= n_q) { e = 1; ra = 0; rb = 0; }
-    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;
+    const unsigned errm = __ballot_sync(0xffffffffu, e != 0);      // every lane votes: no short-circuit around it
+    const bool bad = active && ((errm >> sh) & 63u) != 0;
     if (bad && role == 0) atomicExch(err, 1);
     const bool dead0 = bad || (((b0 >> sh) & 3u) == 3u) || qinf[ra] != 0;
     const bool dead1 = NP == 2 ? (bad || (((b1 >> sh) & 3u) == 3u) || qinf[rb] != 0) : true;
@@ -707,7 +710,8 @@ vm_gt_kernel(int opk, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out
         if (opk == GT_OP_MUL) D.load_coeff(role, 6, b + item * CD::gt_size(), flags & FLAG_IN_MONT, &e);
     }
     const int sh = (gw < B200_VM_GROUPS_PER_WARP ? gw : 0) * VM_G;
-    const bool bad = active && ((__ballot_sync(0xffffffffu, e != 0) >> sh) & 63u) != 0;      // per item, see vm_pairing_kernel
+    const unsigned errm = __ballot_sync(0xffffffffu, e != 0);      // every lane votes: no short-circuit around it
+    const bool bad = active && ((errm >> sh) & 63u) != 0;      // per item, see vm_pairing_kernel
     if (bad && role == 0) atomicExch(err, 1);
     __syncwarp();
     uint32_t fb = 12;

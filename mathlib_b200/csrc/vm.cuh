@@ -133,24 +133,32 @@ struct Vm {
         for (int k = 2; k < W - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
         v[W - 1] = addc(Ev[W - 1], Od[W - 2]);
     }
-    // acc (W words, two's complement while partial sums are pending) +/-= v (2N words)
+    // acc (W words) += v (2N words: one product)
     static B200_HD void wide_add(uint32_t* acc, const uint32_t* v) {
         acc[0] = add_cc(acc[0], v[0]);
 #pragma unroll
         for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], v[k]);
         acc[2 * N] = addc(acc[2 * N], 0);
     }
-    static B200_HD void wide_sub(uint32_t* acc, const uint32_t* v) {
+    // acc +/-= v, W words each
+    static B200_HD void wide_addw(uint32_t* acc, const uint32_t* v) {
+        acc[0] = add_cc(acc[0], v[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], v[k]);
+        acc[2 * N] = addc(acc[2 * N], v[2 * N]);
+    }
+    static B200_HD void wide_subw(uint32_t* acc, const uint32_t* v) {
         acc[0] = sub_cc(acc[0], v[0]);
 #pragma unroll
         for (int k = 1; k < 2 * N; k++) acc[k] = subc_cc(acc[k], v[k]);
-        acc[2 * N] = subc(acc[2 * N], 0);
+        acc[2 * N] = subc(acc[2 * N], v[2 * N]);
     }
     // Montgomery reduction of a wide value T < 4 p R (T[0..2N), top word zero) -> canonical residue T / R mod p.
     // Word-sliding reduction on an even / odd split of T: no data movement, the window offsets are compile-time.
-    // skip2p: the caller guarantees T < p R, so the result is below 2p before the final subtraction (microcode header
-    // flag HDR_SKIP2P, set per phase by the compiler from the number of accumulated products)
-    static B200_HD void redc(E1& r, const uint32_t* Tw, bool skip2p) {
+    // levels: the compiler's bound on the result before canonicalisation -- T < (2^levels - 1) p R, so T/R + p < 2^levels p
+    // and `levels` conditional subtractions (of 4p, 2p, p) make it canonical (microcode header bits 18..19, per phase:
+    // vm/compiler.py dot_bounds)
+    static B200_HD void redc(E1& r, const uint32_t* Tw, uint32_t levels) {
         uint32_t X[AW], Y[AW];
 #pragma unroll
         for (int k = 0; k < 2 * N; k += 2) { X[k] = Tw[k]; X[k + 1] = 0; Y[k] = Tw[k + 1]; Y[k + 1] = 0; }
@@ -189,7 +197,8 @@ struct Vm {
 #pragma unroll
         for (int k = 1; k < N - 1; k++) r.l[k] = addc_cc(Xw[k], Yw[k + 1]);
         r.l[N - 1] = addc(Xw[N - 1], Yw[N]);
-        if (!skip2p) cond_sub_kp(r, 1);
+        if (levels >= 3) cond_sub_kp(r, 2);
+        if (levels >= 2) cond_sub_kp(r, 1);
         cond_sub_kp(r, 0);
     }
     // acc (even aligned, full-size words above) += v_even * m, carry rippled one word up
@@ -272,16 +281,15 @@ struct Vm {
             return;
         }
         if (kind == VM_DOT) {
-            // Karatsuba over Fp2 with lazy reduction: per term v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) (unreduced);
-            //   RE = nt*|BETA|*p^2 + sum (v0 + BETA v1)      IM = sum (v2 - v0 - v1)
-            // the p^2 offset keeps RE non-negative; IM may dip below zero between its updates (two's complement).
-            uint32_t RE[W], IM[W];
-            {
-                const uint32_t* off = C::K().p2 + (nt * (C::BETA == -1 ? 1 : 5)) * (2 * N);
+            // Karatsuba over Fp2 with lazy reduction: per term v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) (unreduced); every
+            // product is folded ONCE into its own wide accumulator (T0 = sum v0, T1 = sum v1, T2 = sum v2) and the combination
+            //   RE = off p^2 + T0 - |BETA| T1        IM = T2 - T0 - T1
+            // happens once per op, followed by ONE Montgomery reduction each.  off p^2 (header bits 24..28: the compiler's
+            // bound on |BETA| sum a1 b1) keeps RE non-negative.  (Folding v0 / v1 into RE and IM per term, as in round 1,
+            // costs two more wide additions per term: 101.4 -> 99.7 ms per 65,536 checks.)
+            uint32_t T0[W], T1[W], T2[W];
 #pragma unroll
-                for (int k = 0; k < 2 * N; k++) { RE[k] = off[k]; IM[k] = 0; }
-                RE[2 * N] = 0; IM[2 * N] = 0;
-            }
+            for (int k = 0; k < W; k++) { T0[k] = 0; T1[k] = 0; T2[k] = 0; }
             for (uint32_t t = 0; t < nt; t++) {
                 const uint32_t tw = w[2 + t];
                 E2 a, b;
@@ -298,13 +306,10 @@ struct Vm {
                 }
                 uint32_t v[2 * N];
                 wide_mul(v, a.c0.l, b.c0.l);               // v0
-                wide_add(RE, v);
+                wide_add(T0, v);
                 if (!real_b) {
-                    wide_sub(IM, v);
                     wide_mul(v, a.c1.l, b.c1.l);           // v1
-                    wide_sub(IM, v);
-                    wide_sub(RE, v);
-                    if (C::BETA == -5) { wide_sub(RE, v); wide_sub(RE, v); wide_sub(RE, v); wide_sub(RE, v); }
+                    wide_add(T1, v);
                     // sums stay below 2p < 2^(32N); formed in place (the halves are dead now)
                     a.c0.l[0] = add_cc(a.c0.l[0], a.c1.l[0]);
 #pragma unroll
@@ -313,15 +318,28 @@ struct Vm {
 #pragma unroll
                     for (int i = 1; i < N; i++) b.c0.l[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
                     wide_mul(v, a.c0.l, b.c0.l);           // v2
-                    wide_add(IM, v);
+                    wide_add(T2, v);
                 } else {
-                    wide_mul(v, a.c1.l, b.c0.l);           // imaginary part a1 * s
-                    wide_add(IM, v);
+                    wide_add(T2, v);                        // real scalar s: (a0 + a1) s = v0 + a1 s
+                    wide_mul(v, a.c1.l, b.c0.l);
+                    wide_add(T2, v);
                 }
             }
-            const bool skip2p = (hdr >> 18) & 1;
-            redc(res.c0, RE, skip2p);
-            redc(res.c1, IM, skip2p);
+            {
+                const uint32_t* off = C::K().p2 + ((hdr >> 24) & 31) * (2 * N);
+                uint32_t RE[W];
+#pragma unroll
+                for (int k = 0; k < 2 * N; k++) RE[k] = off[k];
+                RE[2 * N] = 0;
+                wide_addw(RE, T0);
+                wide_subw(RE, T1);
+                if (C::BETA == -5) { wide_subw(RE, T1); wide_subw(RE, T1); wide_subw(RE, T1); wide_subw(RE, T1); }
+                wide_subw(T2, T0);
+                wide_subw(T2, T1);
+                const uint32_t levels = (hdr >> 18) & 3;
+                redc(res.c0, RE, levels);
+                redc(res.c1, T2, levels);
+            }
             if (scale != 1) { mul_small(res.c0, res.c0, scale); mul_small(res.c1, res.c1, scale); }
         } else {
             T::f2_zero(res);

@@ -409,6 +409,28 @@ class Curve:
         check(fn(self.id, n, buf_ptr(data), out, flags))
         return out.raw[:osz]
 
+    # ---- hash-to-G1 (reference driver/math.go:120-131) ----
+    def HashToG1Batch(self, messages, domain=b"", flags=0):
+        """one G1 point per message (list of bytes); curve ids 3 / 5: RFC 9380 SHA-256 suite, 6 / 7: the BBS variant"""
+        import array
+        lib = load()
+        n = len(messages)
+        offs = array.array("Q", [0])
+        for msg in messages:
+            offs.append(offs[-1] + len(msg))
+        blob = b"".join(messages)
+        out = ctypes.create_string_buffer(max(n * self.G1ByteSize, 1))
+        check(lib.b200_hash_to_g1_batch(self.id, n, buf_ptr(blob) if blob else None, buf_ptr(offs.tobytes()),
+                                        buf_ptr(domain) if domain else None, len(domain), out, flags))
+        sz = self.G1ByteSize
+        return [G1(self, out.raw[i * sz:(i + 1) * sz]) for i in range(n)]
+
+    def HashToG1(self, data):
+        return self.HashToG1Batch([bytes(data)])[0]
+
+    def HashToG1WithDomain(self, data, domain):
+        return self.HashToG1Batch([bytes(data)], bytes(domain))[0]
+
     def MsmBatch(self, pts, scalars, n, flags=0):
         lib = load()
         out = ctypes.create_string_buffer(self.G1ByteSize)

@@ -33,16 +33,56 @@ REAL0, REAL1 = 4, 8                        # B operand only: use component 0 / 1
 C_ABS, C_B1, C_B2, C_B3, C_CONST = 0, 1, 2, 3, 4
 
 KIND_NOP, KIND_DOT, KIND_LIN, KIND_INV = 0, 1, 2, 3
-HDR_SKIP2P = 1 << 18     # header flag: the phase's dot products are short enough that redc's output is already < 2p
+# ---- bounds of the lazy reduction (csrc/vm.cuh: dot_operand / exec_op) ------------------------------------------------
+# A DOT accumulates  RE = off p^2 + sum A0 B0 - |beta| sum A1 B1  and  IM = sum (A0 B1 + A1 B0)  as plain integers and
+# reduces each ONCE.  A, B are the operands after their modifiers; on a field with head room above p (BLS12-381) the
+# interpreter leaves additions unreduced, so A0, A1 are bounded by small multiples of p:
+#     plain (1, 1);  XI (xi = 1 + u): A0 = x0 - x1 + p < 2p, A1 = x0 + x1 < 2p;  DBL doubles both.
+# B operands are canonical (bound 1 per half; a REAL scalar has no second half).  From these the compiler derives, per op,
+#     off    = ceil bound of |beta| sum A1 B1 in units of p^2 (index into the table of k p^2, k <= 30), and
+#     levels = conditional subtractions (of 4p, 2p, p) that canonicalise redc's result T/R + (< p) < 2^levels p,
+# written into the op header (bits 24..28 and 18..19; `levels` is the maximum over the phase so that the lanes agree).
+_field = {'p': None, 'limbs': None, 'beta': -1, 'lazy': False}
 
-# a DOT of nt terms feeds redc with T < 2 nt p^2 (6 nt p^2 when BETA = -5); redc returns T/R + (< p), so for
-# nt < R / (2p) [R / (6p)] the result is below 2p and the interpreter may drop the conditional subtraction of 2p.
-# Set per curve by programs.build_all (BLS12-381: 4, BN254: 2, BLS12-377: 6).
-_skip2p_terms = [0]
+
+def set_field(p, limbs32, beta, lazy):
+    """field parameters of the curve being compiled (programs.build_all): modulus, 32-bit limbs, u^2, lazy modifiers"""
+    _field.update(p=p, limbs=limbs32, beta=beta, lazy=lazy)
 
 
-def set_skip2p_terms(n):
-    _skip2p_terms[0] = n
+def operand_bounds(am):
+    """(bound A0, bound A1) in units of p for an A operand with modifiers am"""
+    b0 = b1 = 1
+    if _field['lazy']:
+        if am & XI:
+            b0 = b1 = 2
+        if am & DBL:
+            b0, b1 = 2 * b0, 2 * b1
+    return b0, b1
+
+
+def dot_bounds(terms):
+    """(off, levels) of a dot product; terms = [(a, am, b, bm)]"""
+    p, R = _field['p'], 1 << (32 * _field['limbs'])
+    ab = -_field['beta']
+    off = kre = kim = ksum = 0
+    for (_, am, _, bm) in terms:
+        a0, a1 = operand_bounds(am)
+        b0, b1 = (1, 0) if bm & (REAL0 | REAL1) else (1, 1)
+        off += ab * a1 * b1
+        kre += a0 * b0
+        kim += a0 * b1 + a1 * b0
+        ksum += (a0 + a1) * (b0 + b1)
+    assert off <= 30, "offset table of k p^2 ends at k = 30"
+    assert ksum * p * p < R * R, "T2 overflows 2N words"
+    k = max(off + kre, kim)                       # redc input < k p^2
+    for levels in (1, 2, 3):
+        # result < k p^2 / R + p  <  2^levels p   <=>   k p < (2^levels - 1) R
+        if k * p < ((1 << levels) - 1) * R and (1 << levels) * p <= R:
+            return off, levels
+    raise AssertionError("dot product too wide for the field's head room: k = %d" % k)
+
+
 OP_WORDS = 12            # header + 6 terms + 4 lin + 1 spare  (fixed size keeps the interpreter trivial)
 
 
@@ -276,7 +316,7 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
         # the widest dot product of the phase: every lane runs the same multi-operand product variant (zero padded),
         # so lanes with fewer terms do not serialise against the others
         pmax = max([len(v.terms) for v in vs if v.kind == 'dot'] + [0])
-        skip2p = HDR_SKIP2P if 0 < pmax <= _skip2p_terms[0] else 0
+        levels = max([dot_bounds(v.terms)[1] for v in vs if v.kind == 'dot'] + [1])
         for v in lanes:
             w = [0] * OP_WORDS
             if v is not None:
@@ -285,8 +325,9 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
                 nl = len(v.lin)
                 alt = enc_operand(loc(v.alt)) if v.alt is not None else 0
                 assert 1 <= v.scale <= 7
+                off = dot_bounds(v.terms)[0] if v.kind == 'dot' else 0
                 w[0] = (k | (nt << 4) | (nl << 8) | (v.scale << 12) | ((1 if v.halve else 0) << 15) | (v.pred << 16) |
-                        (pmax << 20) | skip2p)
+                        (levels << 18) | (pmax << 20) | (off << 24))
                 w[1] = enc_operand(loc(v)) | (alt << 16)
                 for t, (a, am, b, bm) in enumerate(v.terms):
                     w[2 + t] = enc_operand(loc(a)) | (enc_operand(loc(b)) << 11) | (am << 22) | (bm << 26)

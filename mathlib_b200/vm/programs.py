@@ -11,7 +11,7 @@ Slot maps
 The formulas are the ones of csrc/pairing.cuh (SURVEY A.5 doubling / addition steps, sparse line slots, Granger-Scott
 squaring); tests/test_vm_programs.py checks every compiled program against the oracle.
 """
-from .compiler import (ref, const, dot, lin, inv, mul, sqr, compile_program, set_skip2p_terms, NEG, CONJ, XI, DBL, REAL0,
+from .compiler import (ref, const, dot, lin, inv, mul, sqr, compile_program, set_field, NEG, CONJ, XI, DBL, REAL0,
                        REAL1, C_ABS, C_B1, C_B2, C_B3, C_CONST)
 
 T_BASE, Q_BASE = 12, 18
@@ -55,6 +55,13 @@ class Curve:
         self.name, self.twist, self.family, self.btw_is_4xi = name, twist, family, btw_is_4xi
         self.supp = (0, 2, 3) if twist == 'M' else (0, 1, 3)     # powers of w carrying the line coefficients
 
+
+# name -> (p, 32-bit limbs, u^2, lazy operand modifiers)
+FIELDS = {
+    'BN254': (0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47, 8, -1, False),
+    'BLS381': (0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab, 12, -1, False),
+    'BLS377': (0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001, 12, -5, False),
+}
 
 CURVES = {
     'BN254': Curve('BN254', 'D', 'bn', False),
@@ -459,8 +466,9 @@ def build_all(curve_name):
     cv = CURVES[curve_name]
     _cfg['nslots'], _cfg['nregs'] = SLOTCFG[curve_name]
     _cfg['qstride'] = 3 if cv.family == 'bn' else 2
-    # R/(2p) = 4.92 (BLS12-381), 2.65 (BN254); R/(6p) = 25 (BLS12-377, BETA = -5): see compiler.HDR_SKIP2P
-    set_skip2p_terms({'BLS381': 4, 'BN254': 0, 'BLS377': 6}[curve_name])      # BN254: no measurable gain, left off
+    # field parameters for the lazy-reduction bounds (compiler.dot_bounds).  The interpreter's operand modifiers are
+    # canonical on every curve (lazy = False); the unreduced variant measured slower
+    set_field(*FIELDS[curve_name])
     progs = {}
     for np_ in (1, 2):
         progs['INIT%d' % np_] = prog_init(np_)

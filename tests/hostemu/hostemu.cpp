@@ -248,3 +248,11 @@ extern "C" int he_point_codec(int curve, int g2, int op, const uint8_t* in, uint
     if (curve == 1) return g2 ? point_codec_item<BLS381, 1>(op, in, out, flags) : point_codec_item<BLS381, 0>(op, in, out, flags);
     return g2 ? point_codec_item<BLS377, 1>(op, in, out, flags) : point_codec_item<BLS377, 0>(op, in, out, flags);
 }
+
+#include "../../mathlib_b200/csrc/hash_to_g1.cuh"
+// hash-to-G1, one message (hash_to_g1.cuh: the function the kernel runs per thread); curve ids 3 / 5 standard, 6 / 7 BBS
+extern "C" int he_hash_to_g1(int cid, const uint8_t* msg, size_t mlen, const uint8_t* dst, size_t dlen, uint8_t* out) {
+    if (cid != 3 && cid != 5 && cid != 6 && cid != 7) return 1;
+    HashToG1::item(cid == 6 || cid == 7, msg, mlen, dst, dlen, out, false);
+    return 0;
+}

@@ -270,6 +270,51 @@ def test_gt_exp_bilinearity(m):
         assert c.GtExpBatch(c.GenGt.Bytes(), c.order.to_bytes(32, "big"), 1) == c._gt_one
 
 
+# ---- hash-to-G1 -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("cid", [3, 5, 6, 7])
+def test_hash_to_g1_matches_oracle(m, cid):
+    """driver.Curve.HashToG1 / HashToG1WithDomain batches against oracle/hash_to_curve.py (pinned on RFC 9380's known
+    answers and the reference's SWU literals): the messages of reference math_test.go:307-311 and :903-909, every padding
+    boundary of SHA-256 / BLAKE2b, long domains; kilic == gurvy ids like Test381Compat."""
+    from oracle import codec
+    from oracle import hash_to_curve as H
+    from oracle.params import BLS12_381
+    c = m.Curves[cid]
+    var = H.variant_of(cid)
+    msgs = [b"Chase!", b"", b"a", b"Amazing Grace (how sweet the sound)", b"x" * 55, b"y" * 56, b"z" * 63, b"w" * 64, b"v" * 65,
+            b"u" * 119, b"t" * 127, b"s" * 128, b"r" * 129, bytes(range(256)) * 5]
+    for dst in (b"", b"EF", b"powerplant", b"e" * 255):
+        got = c.HashToG1Batch(msgs, dst)
+        for msg, g in zip(msgs, got):
+            assert g.Bytes() == codec.g1_to_bytes(BLS12_381, H.hash_to_g1(msg, dst, var)), (cid, msg[:8], dst[:8])
+    assert c.HashToG1(b"Chase!").Bytes() == codec.g1_to_bytes(BLS12_381, H.hash_to_g1(b"Chase!", b"", var))
+    assert c.HashToG1WithDomain(b"CD", b"EF").Bytes() == codec.g1_to_bytes(BLS12_381, H.hash_to_g1(b"CD", b"EF", var))
+    # Test381Compat (reference math_test.go:903-909): the kilic and gurvy flavours of a curve hash to the same point
+    twin = {3: 5, 5: 3, 6: 7, 7: 6}[cid]
+    assert c.HashToG1(b"Chase!").Bytes() == m.Curves[twin].HashToG1(b"Chase!").Bytes()
+    # a larger batch: 3,000 distinct messages, sampled against the oracle; results usable by the hot path (in G1)
+    many = [b"msg-%d" % i for i in range(3000)]
+    pts = c.HashToG1Batch(many, b"bbs-domain")
+    for i in (0, 1, 999, 2999):
+        assert pts[i].Bytes() == codec.g1_to_bytes(BLS12_381, H.hash_to_g1(many[i], b"bbs-domain", var))
+    assert c.PointCodecBatch(0, 2, b"".join(p.Bytes() for p in pts), len(pts)) == b"\x01" * len(pts)
+    with pytest.raises(m.B200Error):
+        c.HashToG1Batch([b"x"], b"d" * 256)
+
+
+def test_rfc9380_vector_on_device(m):
+    """RFC 9380 J.9.1 known answer straight through the GPU path (suite BLS12381G1_XMD:SHA-256_SSWU_RO_)"""
+    c = m.Curves[5]
+    dst = b"QUUX-V01-CS02-with-BLS12381G1_XMD:SHA-256_SSWU_RO_"
+    got = c.HashToG1Batch([b"", b"abc"], dst)
+    assert got[0].Bytes().hex() == ("052926add2207b76ca4fa57a8734416c8dc95e24501772c814278700eed6d1e4e8cf62d9c09db0fac349612b759e79a1"
+                                    "08ba738453bfed09cb546dbb0783dbb3a5f1f566ed67bb6be0e8c67e2e81a4cc68ee29813bb7994998f3eae0c9c6a265")
+    assert got[1].Bytes().hex() == ("03567bc5ef9c690c2ab2ecdf6a96ef1c139cc0b2f284dca0a9a7943388a49a3aee664ba5379a7655d3c68900be2f6903"
+                                    "0b9c15f3fe6e5cf4211f346271d7b01c8f3b28be689c8429c85b67af215533311f0b8dfaaa154fa6b88176c229f2885d")
+    with pytest.raises(m.B200Error):
+        m.Curves[1].HashToG1(b"x")                  # BN254 / BLS12-377 hash-to-curve is not on this path
+
+
 # ---- SURVEY 8(f) row 2: (de)serialisation and validation on the device --------------------------------------------------
 @pytest.mark.parametrize("cid", CURVE_IDS)
 def test_point_codec_batches(m, cid):

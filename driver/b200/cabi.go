@@ -125,6 +125,32 @@ func gtExpBatch(curve int, n int, a, scalars []byte, flags uint32) []byte {
 	return out
 }
 
+// hashToG1Batch: one G1 point per message, one domain separation tag for the batch (SURVEY 8f-4).
+func hashToG1Batch(curve int, msgs [][]byte, domain []byte, g1Size int) []byte {
+	offs := make([]uint64, len(msgs)+1)
+	total := 0
+	for i, m := range msgs {
+		total += len(m)
+		offs[i+1] = uint64(total)
+	}
+	blob := make([]byte, 0, total)
+	for _, m := range msgs {
+		blob = append(blob, m...)
+	}
+	out := make([]byte, len(msgs)*g1Size)
+	check("HashToG1", C.b200_hash_to_g1_batch(C.int(curve), C.size_t(len(msgs)), ptr(blob), (*C.uint64_t)(unsafe.Pointer(&offs[0])),
+		ptr(domain), C.size_t(len(domain)), ptr(out), 0))
+	return out
+}
+
+// TakeError reports (and clears) the per-device error flag raised by B200_DEVICE_PTRS calls: those calls are
+// asynchronous, so a rejected input zeroes its own item's output instead of failing the call (include/b200.h).
+func TakeError() bool {
+	var had C.int
+	check("take error", C.b200_take_error(&had))
+	return had != 0
+}
+
 // ---- point (de)serialisation and validation batches (SURVEY 8f-2) ----
 
 // pointCodec: op 0 decompress, 1 compress, 2 validate; outElem = bytes per output element.

@@ -34,12 +34,16 @@ func newCurve(id, fpBytes int, order *big.Int, g1Gen, g2Gen []byte) *Curve {
 	return &Curve{CurveBase: common.CurveBase{Modulus: *order}, id: id, fpBytes: fpBytes, g1Gen: g1Gen, g2Gen: g2Gen}
 }
 
-// NewBn254, NewBls12_381 (kilic semantics), NewBls12_381Gurvy, NewBls12_377 mirror the reference constructors
-// (reference driver/gurvy/bn254.go:289, driver/kilic/bls12-381.go:294, driver/gurvy/bls12381/bls12-381.go:441).
-func NewBn254() *Curve         { return newCurve(idBN254, 32, orderBN254, g1GenBN254, g2GenBN254) }
-func NewBls12_381() *Curve     { return newCurve(idBLS12381, 48, orderBLS12381, g1GenBLS12381, g2GenBLS12381) }
-func NewBls12_381Gurvy() *Curve { return newCurve(idBLS12381Gurvy, 48, orderBLS12381, g1GenBLS12381, g2GenBLS12381) }
-func NewBls12_377() *Curve     { return newCurve(idBLS12377Gurvy, 48, orderBLS12377, g1GenBLS12377, g2GenBLS12377) }
+// NewBn254, NewBls12_381 (kilic semantics), NewBls12_381Gurvy, NewBls12_377 and the two BBS flavours mirror the reference
+// constructors (reference driver/gurvy/bn254.go:289, driver/kilic/bls12-381.go:294 and :298 (NewBls12_381BBS),
+// driver/gurvy/bls12381/bls12-381.go:441 and :789 (NewBBSCurve)).  The BBS ids differ from 3 / 5 only in HashToG1
+// (BLAKE2b-512 + big-endian sign rule, reference driver/kilic/custom.go:205-237).
+func NewBn254() *Curve            { return newCurve(idBN254, 32, orderBN254, g1GenBN254, g2GenBN254) }
+func NewBls12_381() *Curve        { return newCurve(idBLS12381, 48, orderBLS12381, g1GenBLS12381, g2GenBLS12381) }
+func NewBls12_381Gurvy() *Curve   { return newCurve(idBLS12381Gurvy, 48, orderBLS12381, g1GenBLS12381, g2GenBLS12381) }
+func NewBls12_377() *Curve        { return newCurve(idBLS12377Gurvy, 48, orderBLS12377, g1GenBLS12377, g2GenBLS12377) }
+func NewBls12_381BBS() *Curve     { return newCurve(idBLS12381BBS, 48, orderBLS12381, g1GenBLS12381, g2GenBLS12381) }
+func NewBls12_381BBSGurvy() *Curve { return newCurve(idBLS12381BBSGur, 48, orderBLS12381, g1GenBLS12381, g2GenBLS12381) }
 
 func (c *Curve) g1Size() int { return 2 * c.fpBytes }
 func (c *Curve) g2Size() int { return 4 * c.fpBytes }
@@ -182,8 +186,24 @@ func (c *Curve) HashToZr(data []byte) driver.Zr {
 	digest := sha256.Sum256(data) // reference driver/common/curve.go:86-92
 	return c.NewZrFromBytes(digest[:])
 }
-func (c *Curve) HashToG1(data []byte) driver.G1                    { panic("b200: HashToG1 is out of scope (SURVEY 8f-4)") }
-func (c *Curve) HashToG1WithDomain(data, domain []byte) driver.G1  { panic("b200: HashToG1 is out of scope (SURVEY 8f-4)") }
-func (c *Curve) HashToG2(data []byte) driver.G2                    { panic("b200: HashToG2 is out of scope (SURVEY 8f-4)") }
-func (c *Curve) HashToG2WithDomain(data, domain []byte) driver.G2  { panic("b200: HashToG2 is out of scope (SURVEY 8f-4)") }
+
+// HashToG1 / HashToG1WithDomain (SURVEY 8f-4): on the BLS12-381 ids the whole pipeline -- expand_message_xmd, SWU,
+// 11-isogeny, cofactor clearing -- runs on the device (b200_hash_to_g1_batch): RFC 9380's SHA-256 suite for ids 3 / 5
+// (reference driver/kilic/bls12-381.go:410-447, driver/gurvy/bls12381/bls12-381.go:652-677), the BLAKE2b / big-endian-sign
+// variant for the BBS ids (reference driver/kilic/bls12-381.go:462-497).  BN254 / BLS12-377 hashing is not on this path.
+func (c *Curve) HashToG1(data []byte) driver.G1 { return c.HashToG1WithDomain(data, []byte{}) }
+func (c *Curve) HashToG1WithDomain(data, domain []byte) driver.G1 {
+	if c.fpBytes != 48 || c.id == idBLS12377Gurvy {
+		panic("b200: HashToG1 is built for the BLS12-381 curve ids only (SURVEY 8f-4)")
+	}
+	return &G1{c: c, raw: hashToG1Batch(c.id, [][]byte{data}, domain, c.g1Size())}
+}
+
+// HashToG1Batch hashes every message with one domain in a single launch (the BBS verify loop of reference
+// perf_test.go:250-261 hashes one message per signature).
+func (c *Curve) HashToG1Batch(msgs [][]byte, domain []byte) []byte {
+	return hashToG1Batch(c.id, msgs, domain, c.g1Size())
+}
+func (c *Curve) HashToG2(data []byte) driver.G2                   { panic("b200: HashToG2 is out of scope (SURVEY 8f-4)") }
+func (c *Curve) HashToG2WithDomain(data, domain []byte) driver.G2 { panic("b200: HashToG2 is out of scope (SURVEY 8f-4)") }
 func (c *Curve) Rand() (io.Reader, error)                          { return rand.Reader, nil }

@@ -138,6 +138,10 @@ func (g *Gt) IsUnity() bool {
 // b200_gt_inv_batch / b200_gt_mul_batch / b200_gt_exp_batch (SURVEY 8f-3).
 func (g *Gt) Inverse()        { g.raw = gtInvBatch(g.c.id, 1, g.raw, 0) }
 func (g *Gt) Mul(a driver.Gt) { g.raw = gtMulBatch(g.c.id, 1, g.raw, a.(*Gt).raw, 0) }
+// Exp: the device ladder takes a 32-byte exponent.  z.Bytes() is the scalar reduced to [0, r) (reference
+// driver/common/big.go:101-113), whereas the reference drivers exponentiate by the raw big.Int (bn254.go:187-191).  The two
+// agree on every element of order r -- i.e. every Gt a protocol sees after FExp; they differ only for raw (pre-FExp)
+// Miller values combined with exponents >= r or negative, which no reference test or caller forms.
 func (g *Gt) Exp(z driver.Zr) driver.Gt {
 	return &Gt{c: g.c, raw: gtExpBatch(g.c.id, 1, g.raw, z.Bytes(), 0)}
 }

@@ -16,6 +16,13 @@ namespace b200 {
 template <int N> struct G1Affine { Fp<N> x, y; };                    // (0,0) = infinity
 template <int N> struct G1XYZZ { Fp<N> x, y, zz, zzz; };             // zz == 0  <=> infinity
 
+// B200_G1_FORMULAS_NOINLINE (diagnostic builds): compile the point formulas out of line
+#if defined(B200_G1_FORMULAS_NOINLINE)
+#define B200_G1_FN B200_HD_NOINLINE
+#else
+#define B200_G1_FN B200_HD
+#endif
+
 template <class C>
 struct G1Ops {
     static constexpr int N = C::N;
@@ -35,7 +42,7 @@ struct G1Ops {
     static B200_HD void neg(Pt& r, const Pt& a) { r.x = a.x; F::neg(r.y, a.y); r.zz = a.zz; r.zzz = a.zzz; }
 
     // p <- 2a for affine a (mdbl-2008-s-1)
-    static B200_HD void dbl_affine(Pt& p, const Aff& a) {
+    static B200_G1_FN void dbl_affine(Pt& p, const Aff& a) {
         if (aff_is_inf(a) || F::is_zero(a.y)) { set_inf(p); return; }
         E U, V, W, S, M, t;
         F::dbl(U, a.y);
@@ -54,7 +61,7 @@ struct G1Ops {
         p.zzz = W;
     }
     // p <- 2p (dbl-2008-s-1)
-    static B200_HD void dbl(Pt& p) {
+    static B200_G1_FN void dbl(Pt& p) {
         if (is_inf(p)) return;
         E U, V, W, S, M, t;
         F::dbl(U, p.y);
@@ -73,7 +80,7 @@ struct G1Ops {
         F::mulx(p.zzz, W, p.zzz);
     }
     // p <- p + a, a affine (madd-2008-s), complete
-    static B200_HD void madd(Pt& p, const Aff& a) {
+    static B200_G1_FN void madd(Pt& p, const Aff& a) {
         if (aff_is_inf(a)) return;
         if (is_inf(p)) { from_affine(p, a); return; }
         E U2, S2, Pp, R, PP, PPP, Q, t;
@@ -99,7 +106,7 @@ struct G1Ops {
         F::mulx(p.zzz, p.zzz, PPP);
     }
     // p <- p + q (add-2008-s), complete
-    static B200_HD void add(Pt& p, const Pt& q) {
+    static B200_G1_FN void add(Pt& p, const Pt& q) {
         if (is_inf(q)) return;
         if (is_inf(p)) { p = q; return; }
         E U1, U2, S1, S2, Pp, R, PP, PPP, Q, t;

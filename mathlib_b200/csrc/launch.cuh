@@ -130,6 +130,16 @@ struct Launch {
 #endif
         return vm_pairing(np, n, g1a, g2a, g1b, g2b, out, flags, err, s);
     }
+    // at most one check per resident warp (148 SMs x 2 blocks x 4 warps): the split kernel's single wave.  Beyond that a
+    // second wave of the split kernel costs as much as one wave of the five-checks-per-warp kernel.
+    static size_t split_max() {
+#if defined(B200_DEV_KNOBS)
+        static long v = getenv("B200_VM_SPLIT_MAX") ? atol(getenv("B200_VM_SPLIT_MAX")) : 148 * 2 * B200_VM_SPLIT_WARPS;
+        return (size_t)v;
+#else
+        return 148 * 2 * B200_VM_SPLIT_WARPS;
+#endif
+    }
     // batches that cannot fill every SM with full-size blocks use the 4-warp variant (20 products per block)
     static bool small_batch(size_t n) { return n < (size_t)148 * vm_warps<C>() * B200_VM_GROUPS_PER_WARP; }
     template <int W>
@@ -177,6 +187,8 @@ struct Launch {
                 if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 1, WS>, at, cs)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_kernel<C, 2, WS>, at, cs)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_fexp_kernel<C, WS>, at, cs)) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_split_kernel<C, 1>, at, (int)vm_split_smem_bytes<C>())) != cudaSuccess) return e;
+                if ((e = cudaFuncSetAttribute(vm_pairing_split_kernel<C, 2>, at, (int)vm_split_smem_bytes<C>())) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_lines_kernel<C, WS>, at, ss)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 1, WX>, at, sb)) != cudaSuccess) return e;
                 if ((e = cudaFuncSetAttribute(vm_pairing_fixed_kernel<C, 2, WX>, at, sb)) != cudaSuccess) return e;
@@ -201,7 +213,15 @@ struct Launch {
         const VmDirEntry* d_dir = nullptr;
         cudaError_t e = vm_setup(&d_words, &d_dir);
         if (e != cudaSuccess) return e;
-        if (small_batch(n)) vm_launch<B200_VM_WARPS_SMALL>(np, n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir, s);
+        if (n <= split_max()) {
+            // fewer checks than resident warps (BASELINE configs[0]): one check per warp, three lanes per role
+            const unsigned nb = (unsigned)((n + B200_VM_SPLIT_WARPS - 1) / B200_VM_SPLIT_WARPS);
+            const size_t smem = vm_split_smem_bytes<C>();
+            if (np == 1)
+                vm_pairing_split_kernel<C, 1><<<nb, B200_VM_SPLIT_WARPS * 32, smem, s>>>(n, g1a, g2a, g1a, g2a, out, flags, err, d_words, d_dir);
+            else
+                vm_pairing_split_kernel<C, 2><<<nb, B200_VM_SPLIT_WARPS * 32, smem, s>>>(n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir);
+        } else if (small_batch(n)) vm_launch<B200_VM_WARPS_SMALL>(np, n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir, s);
         else vm_launch<vm_warps<C>()>(np, n, g1a, g2a, g1b, g2b, out, flags, err, d_words, d_dir, s);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();

@@ -54,7 +54,9 @@ B200_HD void vm_fill_kbank(uint32_t* kb, int idx) {
     for (int i = 0; i < 2 * N; i++) kb[i] = src[i];
 }
 
-template <class C>
+// SPLIT: three lanes per role (vm.cuh split_stage1 / split_stage2) -- the small-batch kernel; `sub` is the lane's index
+// within its role and `xch` the group's exchange scratch (VM_G * 3 * W words)
+template <class C, bool SPLIT = false>
 struct VmDriver {
     static constexpr int N = C::N;
     static constexpr int SW = 2 * N;
@@ -67,6 +69,8 @@ struct VmDriver {
     const uint32_t* words;
     const VmDirEntry* dir;
     int role;                 // device: this lane's role (0..5, or -1 idle); host emulation: ignored
+    int sub = 0;              // SPLIT: lane within the role (0..2)
+    uint32_t* xch = nullptr;  // SPLIT: exchange scratch of the group
 
     B200_HD void sync() {
 #if defined(__CUDA_ARCH__)
@@ -79,10 +83,27 @@ struct VmDriver {
         const uint32_t nph = dir[prog].phases;
         for (uint32_t ph = 0; ph < nph; ph++) {
 #if defined(__CUDA_ARCH__)
-            if (role >= 0) M::exec_op(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, w + (ph * VM_G + role) * VM_OP_WORDS);
+            if (SPLIT) {
+                const uint32_t* ww = w + (ph * VM_G + (role >= 0 ? role : 0)) * VM_OP_WORDS;
+                uint32_t* x = xch + (role >= 0 ? role : 0) * 3 * M::W;
+                if (role >= 0) M::split_stage1(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, ww, sub, x);
+                __syncwarp();
+                if (role >= 0) M::split_stage2(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, ww, sub, x);
+            } else if (role >= 0) {
+                M::exec_op(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, w + (ph * VM_G + role) * VM_OP_WORDS);
+            }
             __syncwarp();
 #else
-            for (int r = 0; r < VM_G; r++) M::exec_op(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, w + (ph * VM_G + r) * VM_OP_WORDS);
+            for (int r = 0; r < VM_G; r++) {
+                const uint32_t* ww = w + (ph * VM_G + r) * VM_OP_WORDS;
+                if (SPLIT) {
+                    uint32_t* x = xch + r * 3 * M::W;
+                    for (int sl = 0; sl < 3; sl++) M::split_stage1(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, ww, sl, x);
+                    for (int sl = 0; sl < 3; sl++) M::split_stage2(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, ww, sl, x);
+                } else {
+                    M::exec_op(ctx.slots, ctx.kbank, b1, b2, b3, ctx.live, ww);
+                }
+            }
 #endif
         }
     }
@@ -510,6 +531,79 @@ vm_pairing_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_
         else D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
     }
 }
+// Small batches (BASELINE configs[0]: 1,024 checks): fewer checks than the GPU has warps, so the run time is the length of
+// ONE check's dependency chain.  This kernel spends three lanes per role -- one Karatsuba product each (vm.cuh split
+// mode) -- and one check per warp: 18 lanes, a third of the multiplier chain per lane.  Bit-identical to vm_pairing_kernel.
+#define B200_VM_SPLIT_WARPS 4
+template <class C>
+__host__ __device__ constexpr size_t vm_split_smem_bytes() {
+    return 4 * ((size_t)B200_VM_SPLIT_WARPS * (vm_group_stride<C>() + VM_G * 3 * (2 * C::N + 1) + 3) + (size_t)VM_KBANK * 2 * C::N +
+                (size_t)VmTables<C>::NWORDS_CORE + VP_COUNT * 2);
+}
+template <class C, int NP>
+__global__ void __launch_bounds__(B200_VM_SPLIT_WARPS * 32, 2)
+vm_pairing_split_kernel(size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                        uint8_t* out, uint32_t flags, int* err, const uint32_t* mc_words, const VmDirEntry* mc_dir) {
+    extern __shared__ uint32_t smem[];
+    constexpr int N = C::N;
+    constexpr int WARPS = B200_VM_SPLIT_WARPS;
+    constexpr int XW = VM_G * 3 * (2 * N + 1) + 3;       // exchange words per group (padded to a multiple of 4)
+    uint32_t* s_slots = smem;
+    uint32_t* s_xch = s_slots + WARPS * vm_group_stride<C>();
+    uint32_t* s_kbank = s_xch + WARPS * XW;
+    uint32_t* s_words = s_kbank + VM_KBANK * 2 * N;
+    VmDirEntry* s_dir = reinterpret_cast<VmDirEntry*>(s_words + VmTables<C>::NWORDS_CORE);
+    for (int i = threadIdx.x; i < VmTables<C>::NWORDS_CORE; i += blockDim.x) s_words[i] = mc_words[i];
+    if (threadIdx.x < VP_COUNT) s_dir[threadIdx.x] = mc_dir[threadIdx.x];
+    if (threadIdx.x < VM_KBANK) vm_fill_kbank<C>(s_kbank + threadIdx.x * 2 * N, threadIdx.x);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = lane < 3 * VM_G ? lane / 3 : -1;     // lanes 18..31 idle
+    const int sub = lane % 3;
+    const size_t item = (size_t)blockIdx.x * WARPS + warp;
+    const bool active = role >= 0 && item < n;
+    const bool lead = active && sub == 0;                  // the lane of a role that does its I/O
+
+    VmDriver<C, true> D;
+    D.ctx.slots = s_slots + (size_t)warp * vm_group_stride<C>();
+    D.ctx.kbank = s_kbank;
+    D.words = s_words;
+    D.dir = s_dir;
+    D.role = active ? role : -1;
+    D.sub = sub;
+    D.xch = s_xch + (size_t)warp * XW;
+    typedef Codec<C> CD;
+    const bool in_mont = flags & FLAG_IN_MONT;
+    int e = 0, z0 = 0, z1 = 0;
+    if (lead) {
+        z0 = D.load_coord(role, 0, g1a + item * CD::g1_size(), g2a + item * CD::g2_size(), in_mont, &e);
+        if (NP == 2) z1 = D.load_coord(role, 1, g1b + item * CD::g1_size(), g2b + item * CD::g2_size(), in_mont, &e);
+    }
+    // lane 3 r speaks for role r
+    const unsigned b0 = __ballot_sync(0xffffffffu, z0 != 0), b1 = __ballot_sync(0xffffffffu, z1 != 0);
+    const unsigned any_err = __ballot_sync(0xffffffffu, e != 0);
+    const bool bad = active && any_err != 0;
+    if (bad && lane == 0) atomicExch(err, 1);
+    auto zero_role = [](unsigned m, int r) { return ((m >> (3 * r)) & 1u) != 0; };
+    const bool pz0 = zero_role(b0, 0) && zero_role(b0, 1), qz0 = zero_role(b0, 2) && zero_role(b0, 3) && zero_role(b0, 4) && zero_role(b0, 5);
+    const bool pz1 = zero_role(b1, 0) && zero_role(b1, 1), qz1 = zero_role(b1, 2) && zero_role(b1, 3) && zero_role(b1, 4) && zero_role(b1, 5);
+    const bool dead0 = bad || pz0 || qz0;
+    const bool dead1 = NP == 2 ? (bad || pz1 || qz1) : true;
+    D.ctx.live = (dead0 ? 0u : 1u) | (dead1 ? 0u : 2u);
+    __syncwarp();
+    uint32_t fb = D.template miller<NP>();
+    if (flags & FLAG_FEXP) fb = D.final_exp(fb);
+    if (flags & FLAG_UNITY) {
+        const bool ok = lead ? D.coeff_is_one_part(role, fb) : true;
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (lead && role == 0) out[item] = (!bad && okm == 0xffffffffu) ? 1 : 0;
+    } else if (lead) {
+        if (bad) D.store_zero_coeff(role, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+        else D.store_coeff(role, fb, out + item * CD::gt_size(), flags & FLAG_OUT_MONT);
+    }
+}
+
 // standalone driver.Curve.FExp on the VM (same slot file / microcode as the pairing kernel)
 template <class C, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 4 ? 2 : 1)

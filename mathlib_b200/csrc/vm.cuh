@@ -358,6 +358,129 @@ struct Vm {
         if (halve) T::f2_halve(res, res);
         store2(dst, res);
     }
+
+    // ---------------------------------------------------------------------------------------------------
+    // split mode (small batches, vm_pairing_split_kernel): THREE lanes per role.  Lane `sub` of a role accumulates ONE of the
+    // three Karatsuba products of every term (sub 0: a0 b0, 1: a1 b1, 2: (a0+a1)(b0+b1)); the wide sums are exchanged
+    // through a shared scratch area, then sub 0 reduces the real part and sub 1 the imaginary part, and each finishes its
+    // own component (scale, linear tail, halving, store).  Same values as exec_op, a third of the multiplier chain per lane.
+    // stage1, a warp barrier, stage2 -- the host emulation runs the three lanes of a stage one after another.
+    // xch: this role's scratch, 3 * W words.
+    // ---------------------------------------------------------------------------------------------------
+    static B200_HD_NOINLINE void split_stage1(uint32_t* slots, const uint32_t* kbank, uint32_t b1, uint32_t b2, uint32_t b3,
+                                              uint32_t live, const uint32_t* w, int sub, uint32_t* xch) {
+        Ctx c;
+        c.slots = slots; c.kbank = kbank; c.base[0] = b1; c.base[1] = b2; c.base[2] = b3; c.live = live;
+        const uint32_t hdr = w[0];
+        if ((hdr & 15) != VM_DOT) return;
+        const uint32_t nt = (hdr >> 4) & 15, pred = (hdr >> 16) & 3;
+        if (pred && !((c.live >> (pred - 1)) & 1)) return;
+        uint32_t Tacc[W];
+#pragma unroll
+        for (int k = 0; k < W; k++) Tacc[k] = 0;
+        for (uint32_t t = 0; t < nt; t++) {
+            const uint32_t tw = w[2 + t];
+            E2 a, b;
+            load2(a, operand_ptr(c, tw & 0x7FF));
+            const uint32_t am = (tw >> 22) & 15;
+            if (am) apply_mod(a, am);
+            const uint32_t bm = (tw >> 26) & 15;
+            load2(b, operand_ptr(c, (tw >> 11) & 0x7FF));
+            if (bm & (VM_REAL0 | VM_REAL1)) {
+                if (bm & VM_REAL1) b.c0 = b.c1;
+                F::zero(b.c1);                               // real scalar s = (s, 0)
+            } else if (bm & 3) {
+                apply_mod(b, bm & 3);
+            }
+            // this lane's factor pair: (a0, b0), (a1, b1) or the plain sums (a0 + a1, b0 + b1) (< 2p each)
+            uint32_t xa[N], xb[N], sa[N], sb[N];
+            sa[0] = add_cc(a.c0.l[0], a.c1.l[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) sa[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
+            sb[0] = add_cc(b.c0.l[0], b.c1.l[0]);
+#pragma unroll
+            for (int i = 1; i < N; i++) sb[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                xa[i] = sub == 0 ? a.c0.l[i] : (sub == 1 ? a.c1.l[i] : sa[i]);
+                xb[i] = sub == 0 ? b.c0.l[i] : (sub == 1 ? b.c1.l[i] : sb[i]);
+            }
+            uint32_t v[2 * N];
+            wide_mul(v, xa, xb);
+            wide_add(Tacc, v);
+        }
+        uint32_t* mine = xch + sub * W;
+#pragma unroll
+        for (int k = 0; k < W; k++) mine[k] = Tacc[k];
+    }
+    static B200_HD_NOINLINE void split_stage2(uint32_t* slots, const uint32_t* kbank, uint32_t b1, uint32_t b2, uint32_t b3,
+                                              uint32_t live, const uint32_t* w, int sub, const uint32_t* xch) {
+        Ctx c;
+        c.slots = slots; c.kbank = kbank; c.base[0] = b1; c.base[1] = b2; c.base[2] = b3; c.live = live;
+        const uint32_t hdr = w[0];
+        const uint32_t kind = hdr & 15;
+        if (kind == VM_NOP || sub == 2) return;
+        const uint32_t nl = (hdr >> 8) & 15;
+        const uint32_t scale = (hdr >> 12) & 7, halve = (hdr >> 15) & 1, pred = (hdr >> 16) & 3;
+        uint32_t* dst = const_cast<uint32_t*>(operand_ptr(c, w[1] & 0x7FF)) + sub * N;        // this lane's component
+        if (pred && !((c.live >> (pred - 1)) & 1)) {
+            const uint32_t* src = operand_ptr(c, (w[1] >> 16) & 0x7FF) + sub * N;
+            for (int i = 0; i < N; i++) dst[i] = src[i];
+            return;
+        }
+        if (kind == VM_INV) {
+            if (sub == 0) {
+                E2 a, res;
+                load2(a, operand_ptr(c, w[2] & 0x7FF));
+                T::f2_inv(res, a);
+                store2(dst, res);
+            }
+            return;
+        }
+        E1 r;
+        if (kind == VM_DOT) {
+            uint32_t V[W], U[W];
+            const uint32_t levels = (hdr >> 18) & 3;
+            if (sub == 0) {                                  // RE = off p^2 + T0 - |BETA| T1
+                const uint32_t* off = C::K().p2 + ((hdr >> 24) & 31) * (2 * N);
+#pragma unroll
+                for (int k = 0; k < 2 * N; k++) V[k] = off[k];
+                V[2 * N] = 0;
+#pragma unroll
+                for (int k = 0; k < W; k++) U[k] = xch[k];
+                wide_addw(V, U);
+#pragma unroll
+                for (int k = 0; k < W; k++) U[k] = xch[W + k];
+                wide_subw(V, U);
+                if (C::BETA == -5) { wide_subw(V, U); wide_subw(V, U); wide_subw(V, U); wide_subw(V, U); }
+            } else {                                         // IM = T2 - T0 - T1
+#pragma unroll
+                for (int k = 0; k < W; k++) { V[k] = xch[2 * W + k]; U[k] = xch[k]; }
+                wide_subw(V, U);
+#pragma unroll
+                for (int k = 0; k < W; k++) U[k] = xch[W + k];
+                wide_subw(V, U);
+            }
+            redc(r, V, levels);
+            if (scale != 1) mul_small(r, r, scale);
+        } else {
+            F::zero(r);
+        }
+        for (uint32_t t = 0; t < nl; t++) {
+            const uint32_t lw = w[8 + t];
+            E2 x;
+            load2(x, operand_ptr(c, lw & 0x7FF));
+            apply_mod(x, (lw >> 16) & 15);
+            E1 xc = sub == 0 ? x.c0 : x.c1;
+            int coef = (int)((lw >> 11) & 31);
+            if (coef >= 16) coef -= 32;
+            const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+            if (mag != 1) mul_small(xc, xc, mag);
+            if (coef < 0) F::sub(r, r, xc); else F::add(r, r, xc);
+        }
+        if (halve) F::halve(r, r);
+        for (int i = 0; i < N; i++) dst[i] = r.l[i];
+    }
 };
 
 }  // namespace b200

@@ -122,14 +122,16 @@ extern "C" int he_pairing_bytes(int curve, int np, const uint8_t* g1a, const uin
 
 #include "../../mathlib_b200/csrc/pairing_vm.cuh"
 #include <vector>
-// VM pairing on the host: lanes of a phase are executed one after another (pairing_vm.cuh, host path of run())
-template <class C> static int t_vm_pair(int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
-                                        uint8_t* out, int fexp) {
+// VM pairing on the host: lanes of a phase are executed one after another (pairing_vm.cuh, host path of run());
+// SPLIT = the three-lanes-per-role mode of the small-batch kernel
+template <class C, bool SPLIT = false> static int t_vm_pair(int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
+                                                           const uint8_t* g2b, uint8_t* out, int fexp) {
     constexpr int N = C::N;
     typedef VmTables<C> TB;
-    std::vector<uint32_t> slots((size_t)TB::NSLOTS * 2 * N, 0u), kb((size_t)VM_KBANK * 2 * N);
+    std::vector<uint32_t> slots((size_t)TB::NSLOTS * 2 * N, 0u), kb((size_t)VM_KBANK * 2 * N), xch((size_t)VM_G * 3 * (2 * N + 1), 0u);
     for (int i = 0; i < VM_KBANK; i++) vm_fill_kbank<C>(kb.data() + (size_t)i * 2 * N, i);
-    VmDriver<C> D;
+    VmDriver<C, SPLIT> D;
+    D.xch = xch.data();
     D.ctx.slots = slots.data();
     D.ctx.kbank = kb.data();
     D.words = TB::host_words();
@@ -155,6 +157,13 @@ extern "C" int he_vm_pairing(int curve, int np, const uint8_t* g1a, const uint8_
     if (curve == 0) return t_vm_pair<BN254>(np, g1a, g2a, g1b, g2b, out, fexp);
     if (curve == 1) return t_vm_pair<BLS381>(np, g1a, g2a, g1b, g2b, out, fexp);
     return t_vm_pair<BLS377>(np, g1a, g2a, g1b, g2b, out, fexp);
+}
+
+extern "C" int he_vm_pairing_split(int curve, int np, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b, const uint8_t* g2b,
+                                   uint8_t* out, int fexp) {
+    if (curve == 0) return t_vm_pair<BN254, true>(np, g1a, g2a, g1b, g2b, out, fexp);
+    if (curve == 1) return t_vm_pair<BLS381, true>(np, g1a, g2a, g1b, g2b, out, fexp);
+    return t_vm_pair<BLS377, true>(np, g1a, g2a, g1b, g2b, out, fexp);
 }
 
 // fixed-Q pairing on the host: line tables of the G2 arguments (precompute_lines), then miller_fixed -- the control flow of

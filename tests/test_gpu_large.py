@@ -70,6 +70,36 @@ def test_msm_random_vs_cpu_oracle(m, cid, n):
     assert c.MsmBatch(g1a, ks, n) == orc.g1_msm(cid, n, g1a, ks)
 
 
+@pytest.mark.parametrize("cid", [1, 3, 4])
+def test_small_batch_split_kernel_is_bit_identical(m, cid):
+    """BASELINE configs[0] shape: batches of at most one check per resident warp (<= 1,184) run the three-lanes-per-role
+    kernel (vm_pairing_split_kernel), larger ones the five-checks-per-warp kernel.  Same inputs, same bytes -- raw Miller
+    value, exponentiated value and unity verdicts, with infinity arguments in both slots."""
+    c = m.Curves[cid]
+    n = 1024
+    g1a, g2a, g1b, g2b, expect = rand_inputs(m, cid, 2 * n, seed=700 + cid)
+    gs, qs, ts = c.G1ByteSize, c.G2ByteSize, c.GtByteSize
+    inf2 = bytearray(qs)
+    if c.fp_bytes == 48:
+        inf2[0] = 0x40
+    g1a = c._g1_inf + g1a[gs:]                              # dead pair a in check 0
+    g2b = g2b[:qs] + bytes(inf2) + g2b[2 * qs:]             # dead pair b in check 1
+    for flags in (0, m.FEXP):
+        big = c.Pairing2Batch(g1a, g2a, g1b, g2b, 2 * n, flags)                                  # 2,048 checks: 6-lane kernel
+        small = c.Pairing2Batch(g1a[:n * gs], g2a[:n * qs], g1b[:n * gs], g2b[:n * qs], n, flags)     # 1,024: split kernel
+        assert small == big[:n * ts]
+        one = c.Pairing2Batch(g1a[:gs], g2a[:qs], g1b[:gs], g2b[:qs], 1, flags)
+        assert one == big[:ts]
+        big1 = c.PairingBatch(g1b, g2a, 2 * n, flags)
+        assert c.PairingBatch(g1b[:n * gs], g2a[:n * qs], n, flags) == big1[:n * ts]
+    ver = c.Pairing2Batch(g1a[:n * gs], g2a[:n * qs], g1b[:n * gs], g2b[:n * qs], n, m.FEXP | m.OUT_UNITY_ONLY)
+    want = list(expect[:n])
+    want[0] = 0 if cid else 0
+    got = list(ver)
+    assert got[2:] == want[2:]
+    assert ver == c.Pairing2Batch(g1a, g2a, g1b, g2b, 2 * n, m.FEXP | m.OUT_UNITY_ONLY)[:n]
+
+
 def test_msm_skewed_scalars(m):
     """small / repeated scalars put most points into a few buckets (the reference tests use MaxInt64 scalars,
     math_test.go:749-771): results must still be exact."""

@@ -107,6 +107,14 @@ def test_vm_pairing(hostemu, cid):
         args = [bytes.fromhex(case[k]) for k in ("g1a", "g2a", "g1b", "g2b")]
         assert hostemu.he_vm_pairing(ec, 2, *args, out, 0) == 0 and out.raw.hex() == case["pairing2"]
         assert hostemu.he_vm_pairing(ec, 2, *args, out, 1) == 0 and out.raw.hex() == case["fexp"]
+    # split mode (three lanes per role: the small-batch kernel) gives the same bytes
+    for case in v["pairing"][:3]:
+        assert hostemu.he_vm_pairing_split(ec, 1, bytes.fromhex(case["g1"]), bytes.fromhex(case["g2"]), None, None, out, 0) == 0
+        assert out.raw.hex() == case["pairing"]
+    for case in v["pairing2"]:
+        args = [bytes.fromhex(case[k]) for k in ("g1a", "g2a", "g1b", "g2b")]
+        assert hostemu.he_vm_pairing_split(ec, 2, *args, out, 0) == 0 and out.raw.hex() == case["pairing2"]
+        assert hostemu.he_vm_pairing_split(ec, 2, *args, out, 1) == 0 and out.raw.hex() == case["fexp"]
 
 
 def test_fp_inverse_and_dot(hostemu):

@@ -163,6 +163,12 @@ int b200_g2_compress_batch(int curve, size_t n, const void* pts, void* compresse
 int b200_g1_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 int b200_g2_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 
+/* Batch affine normalisation (Montgomery's trick, one inversion per 8 points): n Jacobian G1 points given as MONT limbs
+   X | Y | Z (kilic PointG1 [3]fe, reference driver/kilic/bls12-381.go:20-23; gnark G1Jac) -> n affine G1 elements
+   (X / Z^2, Y / Z^3) in BYTES form (what G1.Bytes() returns, reference kilic/bls12-381.go:74-78) or MONT with
+   B200_OUT_MONT.  Z = 0 is the point at infinity. */
+int b200_g1_normalize_batch(int curve, size_t n, const void* jacobian_mont, void* out, uint32_t flags);
+
 /* ---- hash-to-G1 for whole batches: driver.Curve.HashToG1 / HashToG1WithDomain
    (reference driver/math.go:120-131).  BLS12-381 curve ids only:
      3, 5  kilic g1.HashToCurve / gnark bls12381.HashToG1 (reference driver/kilic/bls12-381.go:410-447,

@@ -807,6 +807,13 @@ int b200_g2_validate_batch(int curve, size_t n, const void* in, void* ok_out, ui
     return point_codec_batch(curve, 1, 2, n, in, ok_out, flags);
 }
 
+int b200_g1_normalize_batch(int curve, size_t n, const void* jac_mont, void* out, uint32_t flags) {
+    if (flags & B200_IN_MONT) flags &= ~B200_IN_MONT;          // the input is always Montgomery limbs
+    return elementwise_batch(curve, n, {{jac_mont, 3, nullptr}}, out, 2, flags, 4096,
+                             [](const CurveVTable* vt, size_t m, std::vector<Piece>& p, uint8_t* d_out, uint32_t kf, int*,
+                                cudaStream_t s) { return vt->g1_normalize(m, (const uint32_t*)p[0].dev, d_out, kf, s); });
+}
+
 int b200_hash_to_g1_batch(int curve, size_t n, const void* msgs, const uint64_t* offsets, const void* domain,
                           size_t domain_len, void* out, uint32_t flags) {
     if (int rc = ensure_init()) return rc;

@@ -66,6 +66,8 @@ struct CurveVTable {
     // point decompression (op 0) / compression (1) / validation (2) batches, g2 = 0 / 1
     cudaError_t (*point_codec)(int g2, int op, size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err,
                                cudaStream_t s);
+    // batch affine normalisation of Jacobian G1 points (Montgomery's trick)
+    cudaError_t (*g1_normalize)(size_t n, const uint32_t* jac, uint8_t* out, uint32_t flags, cudaStream_t s);
     // hash-to-G1 batch (BLS12-381 only; nullptr on the other curves)
     cudaError_t (*hash_to_g1)(int bbs, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst, size_t dlen,
                               uint8_t* out, uint32_t flags, cudaStream_t s);
@@ -323,6 +325,12 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
+    static cudaError_t g1_normalize(size_t n, const uint32_t* jac, uint8_t* out, uint32_t flags, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        g1_normalize_kernel<C><<<blocks_for((n + B200_NORM_BATCH - 1) / B200_NORM_BATCH, 64), 64, 0, s>>>(n, jac, out, flags);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
     static cudaError_t hash_to_g1(int bbs, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst,
                                   size_t dlen, uint8_t* out, uint32_t flags, cudaStream_t s) {
         if (n == 0) return cudaSuccess;
@@ -462,7 +470,7 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
-                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec,
+                                      &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec, &g1_normalize,
                                       (C::N == 12 && C::BETA == -1) ? &hash_to_g1 : nullptr, &msm_points, &msm_tables, &msm};
         return &t;
     }

@@ -275,6 +275,53 @@ B200_HD int point_codec_item(int op, const uint8_t* in, uint8_t* out, uint32_t f
     return 0;
 }
 
+// Batch affine normalisation with Montgomery's trick: Jacobian (X, Y, Z) -> affine (X / Z^2, Y / Z^3)
+// for BATCH points per thread with ONE field inversion -- the device side of `Bytes()` / `BatchJacobianToAffine` over slabs of
+// kilic PointG1 [3]fe (reference driver/kilic/bls12-381.go:20-23, 74-78) or gnark G1Jac values.  Input: Montgomery limbs
+// X | Y | Z per point; Z = 0 is the point at infinity (-> (0, 0)).  Output: G1 BYTES or MONT.
+#define B200_NORM_BATCH 8
+template <class C>
+B200_HD void g1_normalize_items(size_t n_items, const uint32_t* in, uint8_t* out, bool out_mont) {
+    typedef FpOps<C> F;
+    typedef Fp<C::N> E;
+    constexpr int N = C::N;
+    E z[B200_NORM_BATCH], pre[B200_NORM_BATCH], acc, inv;
+    F::one(acc);
+    for (size_t k = 0; k < n_items; k++) {
+        for (int i = 0; i < N; i++) z[k].l[i] = in[(k * 3 + 2) * N + i];
+        pre[k] = acc;                                   // product of the non-zero Z's before this one
+        if (!F::is_zero(z[k])) F::mulx(acc, acc, z[k]);
+    }
+    F::inv(inv, acc);
+    for (size_t kk = n_items; kk > 0; kk--) {
+        const size_t k = kk - 1;
+        E x, y;
+        F::zero(x); F::zero(y);
+        if (!F::is_zero(z[k])) {
+            E zi, zi2, zi3, X, Y;
+            F::mulx(zi, inv, pre[k]);                   // 1 / Z_k
+            F::mulx(inv, inv, z[k]);                    // drop Z_k from the running inverse
+            for (int i = 0; i < N; i++) { X.l[i] = in[(k * 3) * N + i]; Y.l[i] = in[(k * 3 + 1) * N + i]; }
+            F::sqrx(zi2, zi);
+            F::mulx(zi3, zi2, zi);
+            F::mulx(x, X, zi2);
+            F::mulx(y, Y, zi3);
+        }
+        Codec<C>::g1_store(out + k * Codec<C>::g1_size(), x, y, out_mont);
+    }
+}
+
+#if defined(__CUDACC__)
+template <class C>
+__global__ void __launch_bounds__(64)
+g1_normalize_kernel(size_t n, const uint32_t* in, uint8_t* out, uint32_t flags) {
+    const size_t first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * B200_NORM_BATCH;
+    if (first >= n) return;
+    const size_t cnt = n - first < B200_NORM_BATCH ? n - first : B200_NORM_BATCH;
+    g1_normalize_items<C>(cnt, in + first * 3 * C::N, out + first * Codec<C>::g1_size(), flags & FLAG_OUT_MONT);
+}
+#endif
+
 #if defined(__CUDACC__)
 #define B200_PT_THREADS 64
 template <class C, int G2>

@@ -409,6 +409,13 @@ class Curve:
         check(fn(self.id, n, buf_ptr(data), out, flags))
         return out.raw[:osz]
 
+    def G1NormalizeBatch(self, jacobian_mont, n, flags=0):
+        """n Jacobian points (Montgomery limbs X|Y|Z) -> affine Bytes() (batch normalisation)"""
+        lib = load()
+        out = ctypes.create_string_buffer(max(n * self.G1ByteSize, 1))
+        check(lib.b200_g1_normalize_batch(self.id, n, buf_ptr(jacobian_mont), out, flags))
+        return out.raw[:n * self.G1ByteSize]
+
     # ---- hash-to-G1 (SURVEY 8f-4; reference driver/math.go:120-131) ----
     def HashToG1Batch(self, messages, domain=b"", flags=0):
         """one G1 point per message (list of bytes); curve ids 3 / 5: RFC 9380 SHA-256 suite, 6 / 7: the BBS variant"""

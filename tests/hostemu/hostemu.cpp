@@ -265,3 +265,10 @@ extern "C" int he_hash_to_g1(int cid, const uint8_t* msg, size_t mlen, const uin
     HashToG1::item(cid == 6 || cid == 7, msg, mlen, dst, dlen, out, false);
     return 0;
 }
+
+// batch affine normalisation of Jacobian points (points.cuh: one thread's batch)
+extern "C" void he_g1_normalize(int curve, size_t n, const uint32_t* jac, uint8_t* out) {
+    if (curve == 0) g1_normalize_items<BN254>(n, jac, out, false);
+    else if (curve == 1) g1_normalize_items<BLS381>(n, jac, out, false);
+    else g1_normalize_items<BLS377>(n, jac, out, false);
+}

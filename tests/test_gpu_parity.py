@@ -270,6 +270,33 @@ def test_gt_exp_bilinearity(m):
         assert c.GtExpBatch(c.GenGt.Bytes(), c.order.to_bytes(32, "big"), 1) == c._gt_one
 
 
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_batch_normalisation(m, cid):
+    """b200_g1_normalize_batch: Jacobian (X, Y, Z) Montgomery slabs -> affine Bytes(), one inversion per 8 points; ragged
+    batch size, infinities, against the oracle's encoding."""
+    import random
+    import numpy as np
+    from oracle import codec
+    from oracle.pairing import Pairing
+    from oracle.params import CURVE_IDS as ORACLE_IDS
+    c = m.Curves[cid]
+    P, _ = ORACLE_IDS[cid]
+    C = Pairing(P).C
+    R = 1 << (32 * P.limbs32)
+    rnd = random.Random(70 + cid)
+    n = 1003
+    base = [C.g1_mul(C.g1, rnd.randrange(1, P.r)) for _ in range(16)]
+    words, want = [], b""
+    for i in range(n):
+        pt = None if i % 97 == 5 else base[i % 16]
+        z = rnd.randrange(1, P.p)
+        vals = (rnd.randrange(P.p), rnd.randrange(P.p), 0) if pt is None else (pt[0] * z * z % P.p, pt[1] * z ** 3 % P.p, z)
+        for v in vals:
+            words.append((v * R % P.p).to_bytes(4 * P.limbs32, "little"))
+        want += codec.g1_to_bytes(P, pt)
+    assert c.G1NormalizeBatch(b"".join(words), n) == want
+
+
 # ---- SURVEY 8(f) row 4: hash-to-G1 -----------------------------------------------------------------------------------
 @pytest.mark.parametrize("cid", [3, 5, 6, 7])
 def test_hash_to_g1_matches_oracle(m, cid):

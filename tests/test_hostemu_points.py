@@ -123,3 +123,40 @@ def test_g2_roundtrip_and_rejects(hostemu, cid):
     hostemu.he_point_codec(ec, 1, 2, unc.raw, ok, 0)
     assert ok.raw == b"\x00"
     assert hostemu.he_point_codec(ec, 1, 0, bytes(cb), unc, 0) == 1
+
+
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_batch_normalisation_on_host(hostemu, cid):
+    """Montgomery-trick normalisation of Jacobian points: random Z, an infinity in the middle, batch sizes
+    1..8 -- bytes equal the oracle's affine encoding."""
+    import random
+    import ctypes
+    from oracle import codec
+    from oracle.pairing import Pairing
+    from oracle.params import CURVE_IDS
+    P, _ = CURVE_IDS[cid]
+    C = Pairing(P).C
+    ec = {1: 0, 5: 1, 4: 2}[cid]
+    n32 = P.limbs32
+    R = 1 << (32 * n32)
+    rnd = random.Random(60 + cid)
+
+    def mont_words(v):
+        v = v * R % P.p
+        return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(n32)]
+    for n in (1, 2, 5, 8):
+        pts = [C.g1_mul(C.g1, rnd.randrange(1, P.r)) for _ in range(n)]
+        if n >= 5:
+            pts[2] = None
+        words, want = [], b""
+        for pt in pts:
+            z = rnd.randrange(1, P.p)
+            if pt is None:
+                words += mont_words(rnd.randrange(P.p)) + mont_words(rnd.randrange(P.p)) + [0] * n32
+            else:
+                words += mont_words(pt[0] * z * z % P.p) + mont_words(pt[1] * z * z * z % P.p) + mont_words(z)
+            want += codec.g1_to_bytes(P, pt)
+        arr = (ctypes.c_uint32 * len(words))(*words)
+        out = ctypes.create_string_buffer(n * 2 * P.fp_bytes)
+        hostemu.he_g1_normalize(ec, ctypes.c_size_t(n), arr, out)
+        assert out.raw == want

@@ -67,6 +67,7 @@ struct BN254 {
     static constexpr int FP_BYTES = 32;
     static constexpr int BETA = -1;                   // u^2
     static constexpr int XI0 = 9, XI1 = 1;            // xi = 9 + u
+    static constexpr bool LAZY_MODS = false;          // VM operand modifiers stay canonical (2 spare bits, xi = 9 + u)
     static constexpr TwistType TWIST = TWIST_D;
     static constexpr Family FAMILY = FAMILY_BN;
     static constexpr uint64_t X_ABS = 4965661367192848881ull;
@@ -86,6 +87,7 @@ struct BLS381 {
     static constexpr int FP_BYTES = 48;
     static constexpr int BETA = -1;
     static constexpr int XI0 = 1, XI1 = 1;            // xi = 1 + u
+    static constexpr bool LAZY_MODS = true;           // VM operand modifiers unreduced: 8p < 2^384 (vm.cuh lazy_mods)
     static constexpr TwistType TWIST = TWIST_M;
     static constexpr Family FAMILY = FAMILY_BLS12;
     static constexpr uint64_t X_ABS = 0xd201000000010000ull;
@@ -105,6 +107,7 @@ struct BLS377 {
     static constexpr int FP_BYTES = 48;
     static constexpr int BETA = -5;
     static constexpr int XI0 = 0, XI1 = 1;            // xi = u
+    static constexpr bool LAZY_MODS = false;
     static constexpr TwistType TWIST = TWIST_D;
     static constexpr Family FAMILY = FAMILY_BLS12;
     static constexpr uint64_t X_ABS = 0x8508c00000000001ull;

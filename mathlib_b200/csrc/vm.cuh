@@ -133,6 +133,109 @@ struct Vm {
         for (int k = 2; k < W - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
         v[W - 1] = addc(Ev[W - 1], Od[W - 2]);
     }
+    // T[0..2N) += a * b, in place.  T itself is the even-aligned accumulator of the operand scanning above (its words may be
+    // full: every chain below is a carry chain over the words it touches); the odd-aligned partial sums go to a fresh Od
+    // (Od[k] = word k + 1) that is merged once at the end.  The carry that leaves the top of a row's chain -- T's or Od's --
+    // is deposited in Od one word above the chain: up there Od holds nothing but earlier carries, so the deposit cannot
+    // overflow and the next rows' chains absorb it.  144 IMAD.WIDE + 22 deposits + 23 merge additions per product, no
+    // separate product array and no wide addition (wide_mul + wide_add: 25 more instructions and 24 more registers).
+    // The sum stays below 2^(64N) by the compiler's bounds (dot_bounds), so nothing leaves word 2N - 1.
+    static B200_HD void wide_mac(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+        uint32_t Od[2 * N - 1];
+        // row 0: T's chain accumulates, Od starts from plain products
+        T[0] = mad_lo_cc(a[0], b[0], T[0]);
+        T[1] = madc_hi_cc(a[0], b[0], T[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            T[j] = madc_lo_cc(a[j], b[0], T[j]);
+            T[j + 1] = madc_hi_cc(a[j], b[0], T[j + 1]);
+        }
+        const uint32_t c0 = addc(0, 0);               // word N
+#pragma unroll
+        for (int j = 1; j < N; j += 2) {
+            Od[j - 1] = mul_lo(a[j], b[0]);
+            Od[j] = mul_hi(a[j], b[0]);
+        }
+        Od[N - 1] += c0;                              // hi <= 2^32 - 2: no overflow
+#pragma unroll
+        for (int k = N; k < 2 * N - 1; k++) Od[k] = 0;
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const int je = i & 1;          // first j with (i+j) even
+            const int jo = je ^ 1;         // first j with (i+j) odd
+            {
+                const int w0 = i + je;
+                T[w0] = mad_lo_cc(a[je], b[i], T[w0]);
+                T[w0 + 1] = madc_hi_cc(a[je], b[i], T[w0 + 1]);
+#pragma unroll
+                for (int j = je + 2; j < N; j += 2) {
+                    T[i + j] = madc_lo_cc(a[j], b[i], T[i + j]);
+                    T[i + j + 1] = madc_hi_cc(a[j], b[i], T[i + j + 1]);
+                }
+                if (w0 + N - 1 < 2 * N - 1) Od[w0 + N - 1] = addc(Od[w0 + N - 1], 0);        // word w0 + N
+            }
+            {
+                const int w0 = i + jo - 1;
+                Od[w0] = mad_lo_cc(a[jo], b[i], Od[w0]);
+                Od[w0 + 1] = madc_hi_cc(a[jo], b[i], Od[w0 + 1]);
+#pragma unroll
+                for (int j = jo + 2; j < N; j += 2) {
+                    Od[i + j - 1] = madc_lo_cc(a[j], b[i], Od[i + j - 1]);
+                    Od[i + j] = madc_hi_cc(a[j], b[i], Od[i + j]);
+                }
+                if (w0 + N < 2 * N - 1) Od[w0 + N] = addc(Od[w0 + N], 0);
+            }
+        }
+        T[1] = add_cc(T[1], Od[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], Od[k - 1]);
+        T[2 * N - 1] = addc(T[2 * N - 1], Od[2 * N - 2]);
+    }
+    // one half (N words) of a slot
+    static B200_HD void load1(E1& r, const uint32_t* p) {
+        const Q4* q = reinterpret_cast<const Q4*>(p);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) {
+            Q4 a = q[i];
+            r.l[4 * i] = a.x; r.l[4 * i + 1] = a.y; r.l[4 * i + 2] = a.z; r.l[4 * i + 3] = a.w;
+        }
+    }
+    // plain integer helpers on N words (no reduction): the lazy operand modifiers below
+    static B200_HD void add_nr(E1& r, const E1& a, const E1& b) {
+        r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+        r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);
+    }
+    static B200_HD void p_minus(E1& r, const E1& a) {       // p - a for a <= p
+        const uint32_t* p = C::p();
+        r.l[0] = sub_cc(p[0], a.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(p[i], a.l[i]);
+        r.l[N - 1] = subc(p[N - 1], a.l[N - 1]);
+    }
+    static B200_HD void p_minus_c(E1& x) { p_minus(x, x); }
+    static B200_HD void shl1(E1& r) {
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) r.l[i] = (r.l[i] << 1) | (r.l[i - 1] >> 31);
+        r.l[0] <<= 1;
+    }
+    // Operand modifiers WITHOUT reduction (curves whose modulus leaves >= 3 spare bits in N words and xi = 1 + u): the halves
+    // stay plain integers below 4p (compiler.operand_bounds tracks the bound; the wide accumulators and the offset k p^2
+    // are sized for it).  Negations first -- they commute with the linear maps that follow and p - x keeps the bound 1:
+    //   NEG: (p - x0, p - x1)   CONJ: (x0, p - x1)   XI: (x0 - x1 + p, x0 + x1)   DBL: (2 x0, 2 x1)
+    static B200_HD void lazy_mods(E1& a0, E1& a1, uint32_t m) {
+        if (m & VM_NEG) p_minus(a0, a0);
+        if (((m & VM_NEG) != 0) != ((m & VM_CONJ) != 0)) p_minus(a1, a1);
+        if (m & VM_XI) {
+            E1 s, d;
+            add_nr(s, a0, a1);
+            p_minus(d, a1);
+            add_nr(a0, a0, d);
+            a1 = s;
+        }
+        if (m & VM_DBL) { shl1(a0); shl1(a1); }
+    }
     // acc (W words) += v (2N words: one product)
     static B200_HD void wide_add(uint32_t* acc, const uint32_t* v) {
         acc[0] = add_cc(acc[0], v[0]);
@@ -256,104 +359,201 @@ struct Vm {
     // ---------------------------------------------------------------------------------------------------
     // one op
     // ---------------------------------------------------------------------------------------------------
+    // acc +/-= v over 2N words (no carry out by construction)
+    static B200_HD void wide_add2n(uint32_t* acc, const uint32_t* v) {
+        acc[0] = add_cc(acc[0], v[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) acc[k] = addc_cc(acc[k], v[k]);
+        acc[2 * N - 1] = addc(acc[2 * N - 1], v[2 * N - 1]);
+    }
+    static B200_HD void wide_sub2n(uint32_t* acc, const uint32_t* v) {
+        acc[0] = sub_cc(acc[0], v[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) acc[k] = subc_cc(acc[k], v[k]);
+        acc[2 * N - 1] = subc(acc[2 * N - 1], v[2 * N - 1]);
+    }
+    // v (2N words) *= c for the small scales the programs use (1, 2, 3, 4, 6); the compiler's bound keeps c v below 2^(64N)
+    static B200_HD void wide_scale(uint32_t* v, uint32_t c) {
+        if (c == 3 || c == 6) {
+            uint32_t d[2 * N];
+#pragma unroll
+            for (int k = 2 * N - 1; k > 0; k--) d[k] = (v[k] << 1) | (v[k - 1] >> 31);
+            d[0] = v[0] << 1;
+            wide_add2n(v, d);
+        }
+        if (c == 2 || c == 6 || c == 4) {
+#pragma unroll
+            for (int k = 2 * N - 1; k > 0; k--) v[k] = (v[k] << 1) | (v[k - 1] >> 31);
+            v[0] <<= 1;
+        }
+        if (c == 4) {
+#pragma unroll
+            for (int k = 2 * N - 1; k > 0; k--) v[k] = (v[k] << 1) | (v[k - 1] >> 31);
+            v[0] <<= 1;
+        }
+    }
+    // x (N words, plain integer) *= c, c in 1..4, no reduction
+    static B200_HD void small_multiple_nr(E1& x, uint32_t c) {
+        if (c == 3) {
+            E1 d = x;
+            shl1(d);
+            add_nr(x, x, d);
+        } else {
+            if (c >= 2) shl1(x);
+            if (c == 4) shl1(x);
+        }
+    }
+    // v[N..2N) += x: adds x R to the value under reduction, i.e. x to the reduced result
+    static B200_HD void wide_add_high(uint32_t* v, const E1& x) {
+        v[N] = add_cc(v[N], x.l[0]);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) v[N + k] = addc_cc(v[N + k], x.l[k]);
+        v[2 * N - 1] = addc(v[2 * N - 1], x.l[N - 1]);
+    }
+    // slot address without branches: the three run-time bases travel packed in one word (byte k = base of class k, byte 0 = 0)
+#if defined(__CUDA_ARCH__)
+    typedef uint32_t kboff_t;        // shared-memory word offset of the constant bank from the group's slot file
+#else
+    typedef long long kboff_t;       // host emulation: two unrelated allocations
+#endif
+    static B200_HD const uint32_t* slot_ptr(const uint32_t* slots, kboff_t kb_off, uint32_t bases, uint32_t o) {
+        const uint32_t cls = (o >> 8) & 7, idx = o & 255;
+        const uint32_t b = (bases >> (8 * (cls & 3))) & 255;
+        return slots + (b + idx) * SLOT_WORDS + (cls == VM_C_CONST ? kb_off : (kboff_t)0);
+    }
+
     static B200_HD_NOINLINE void exec_op(uint32_t* slots, const uint32_t* kbank, uint32_t b1, uint32_t b2, uint32_t b3,
                                          uint32_t live, const uint32_t* w) {
-        Ctx c;
-        c.slots = slots; c.kbank = kbank; c.base[0] = b1; c.base[1] = b2; c.base[2] = b3; c.live = live;
+        const uint32_t bases = (b1 << 8) | (b2 << 16) | (b3 << 24);
+        const kboff_t kb_off = (kboff_t)(kbank - slots);       // the constant bank lies behind the slot files
         const uint32_t hdr = w[0];
         const uint32_t kind = hdr & 15;
         if (kind == VM_NOP) return;
         const uint32_t nt = (hdr >> 4) & 15, nl = (hdr >> 8) & 15;
         const uint32_t scale = (hdr >> 12) & 7, halve = (hdr >> 15) & 1, pred = (hdr >> 16) & 3;
-        uint32_t* dst = const_cast<uint32_t*>(operand_ptr(c, w[1] & 0x7FF));
-        if (pred && !((c.live >> (pred - 1)) & 1)) {
+        uint32_t* dst = const_cast<uint32_t*>(slot_ptr(slots, kb_off, bases, w[1] & 0x7FF));
+        if (pred && !((live >> (pred - 1)) & 1)) {
             E2 t;
-            load2(t, operand_ptr(c, (w[1] >> 16) & 0x7FF));
+            load2(t, slot_ptr(slots, kb_off, bases, (w[1] >> 16) & 0x7FF));
             store2(dst, t);
             return;
         }
         E2 res;
         if (kind == VM_INV) {
             E2 a;
-            load2(a, operand_ptr(c, w[2] & 0x7FF));
+            load2(a, slot_ptr(slots, kb_off, bases, w[2] & 0x7FF));
             T::f2_inv(res, a);
             store2(dst, res);
             return;
         }
+        bool folded = false;
         if (kind == VM_DOT) {
             // Karatsuba over Fp2 with lazy reduction: per term v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) (unreduced); every
-            // product is folded ONCE into its own wide accumulator (T0 = sum v0, T1 = sum v1, T2 = sum v2) and the combination
+            // product is accumulated IN PLACE into its own wide accumulator (T0 = sum v0, T1 = sum v1, T2 = sum v2; wide_mac)
+            // and the combination
             //   RE = off p^2 + T0 - |BETA| T1        IM = T2 - T0 - T1
             // happens once per op, followed by ONE Montgomery reduction each.  off p^2 (header bits 24..28: the compiler's
-            // bound on |BETA| sum a1 b1) keeps RE non-negative.  (Folding v0 / v1 into RE and IM per term, as in round 1,
-            // costs two more wide additions per term: 101.4 -> 99.7 ms per 65,536 checks.)
-            uint32_t T0[W], T1[W], T2[W];
+            // bound on |BETA| sum a1 b1) keeps RE non-negative.
+            // The SM sub-partition dispatches one IMAD.WIDE per 4 cycles and one other integer instruction per ~2 cycles and
+            // does not overlap the two (measured: run time = 4 x IMAD.WIDE + 1.9 x others, summed over the resident warps,
+            // from two warps per sub-partition on), so every instruction removed here is run time.
+            uint32_t T0[2 * N], T1[2 * N], T2[2 * N];
 #pragma unroll
-            for (int k = 0; k < W; k++) { T0[k] = 0; T1[k] = 0; T2[k] = 0; }
+            for (int k = 0; k < 2 * N; k++) { T0[k] = 0; T1[k] = 0; T2[k] = 0; }
             for (uint32_t t = 0; t < nt; t++) {
                 const uint32_t tw = w[2 + t];
-                E2 a, b;
-                load2(a, operand_ptr(c, tw & 0x7FF));
-                const uint32_t am = (tw >> 22) & 15;
-                if (am) apply_mod(a, am);
-                const uint32_t bm = (tw >> 26) & 15;
-                load2(b, operand_ptr(c, (tw >> 11) & 0x7FF));
-                const bool real_b = (bm & (VM_REAL0 | VM_REAL1)) != 0;
-                if (real_b) {
-                    if (bm & VM_REAL1) b.c0 = b.c1;
-                } else if (bm & 3) {
-                    apply_mod(b, bm & 3);
-                }
-                uint32_t v[2 * N];
-                wide_mul(v, a.c0.l, b.c0.l);               // v0
-                wide_add(T0, v);
-                if (!real_b) {
-                    wide_mul(v, a.c1.l, b.c1.l);           // v1
-                    wide_add(T1, v);
-                    // sums stay below 2p < 2^(32N); formed in place (the halves are dead now)
-                    a.c0.l[0] = add_cc(a.c0.l[0], a.c1.l[0]);
-#pragma unroll
-                    for (int i = 1; i < N; i++) a.c0.l[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
-                    b.c0.l[0] = add_cc(b.c0.l[0], b.c1.l[0]);
-#pragma unroll
-                    for (int i = 1; i < N; i++) b.c0.l[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
-                    wide_mul(v, a.c0.l, b.c0.l);           // v2
-                    wide_add(T2, v);
+                const uint32_t* pa = slot_ptr(slots, kb_off, bases, tw & 0x7FF);
+                const uint32_t* pb = slot_ptr(slots, kb_off, bases, (tw >> 11) & 0x7FF);
+                const uint32_t am = (tw >> 22) & 15, bm = (tw >> 26) & 15;
+                E1 a0, a1, b0;
+                if (C::LAZY_MODS) {
+                    load1(a0, pa);
+                    load1(a1, pa + N);
+                    if (am) lazy_mods(a0, a1, am);
                 } else {
-                    wide_add(T2, v);                        // real scalar s: (a0 + a1) s = v0 + a1 s
-                    wide_mul(v, a.c1.l, b.c0.l);
-                    wide_add(T2, v);
+                    E2 a;
+                    load2(a, pa);
+                    if (am) apply_mod(a, am);
+                    a0 = a.c0; a1 = a.c1;
                 }
+                const bool real_b = (bm & (VM_REAL0 | VM_REAL1)) != 0;
+                load1(b0, pb + ((bm & VM_REAL1) ? N : 0));
+                if (!real_b && (bm & VM_NEG)) p_minus_c(b0);
+                wide_mac(T0, a0.l, b0.l);                       // v0 = a0 b0
+                if (!real_b) {
+                    E1 b1;
+                    load1(b1, pb + N);
+                    if (((bm & VM_NEG) != 0) != ((bm & VM_CONJ) != 0)) p_minus_c(b1);
+                    wide_mac(T1, a1.l, b1.l);                   // v1 = a1 b1
+                    add_nr(b0, b0, b1);                         // plain sums: below 2^(32N) by the compiler's bounds
+                }
+                add_nr(a0, a0, a1);
+                wide_mac(T2, a0.l, b0.l);                       // v2 = (a0 + a1)(b0 + b1), or (a0 + a1) s for a real scalar s
             }
             {
                 const uint32_t* off = C::K().p2 + ((hdr >> 24) & 31) * (2 * N);
-                uint32_t RE[W];
+                // T0 := RE = off + T0 - |BETA| T1,  T2 := IM = T2 - (T0 + T1)
+                wide_sub2n(T2, T0);
+                wide_sub2n(T2, T1);
+                {
+                    uint32_t o[2 * N];
 #pragma unroll
-                for (int k = 0; k < 2 * N; k++) RE[k] = off[k];
-                RE[2 * N] = 0;
-                wide_addw(RE, T0);
-                wide_subw(RE, T1);
-                if (C::BETA == -5) { wide_subw(RE, T1); wide_subw(RE, T1); wide_subw(RE, T1); wide_subw(RE, T1); }
-                wide_subw(T2, T0);
-                wide_subw(T2, T1);
+                    for (int k = 0; k < 2 * N; k++) o[k] = off[k];
+                    wide_add2n(T0, o);
+                }
+                wide_sub2n(T0, T1);
+                if (C::BETA == -5) { wide_sub2n(T0, T1); wide_sub2n(T0, T1); wide_sub2n(T0, T1); wide_sub2n(T0, T1); }
+                folded = ((hdr >> 29) & 1) != 0;
+                if (folded) {
+                    // scale and linear tail BEFORE the reduction (compiler.fold_bounds): c redc(V) = redc(c V), and adding
+                    // x R to V adds x to redc(V) -- small multiples of unreduced operands into the high halves of RE / IM
+                    // instead of modular doublings, additions and subtractions on the results
+                    if (scale != 1) { wide_scale(T0, scale); wide_scale(T2, scale); }
+                    for (uint32_t t = 0; t < nl; t++) {
+                        const uint32_t lw = w[8 + t];
+                        const uint32_t* px = slot_ptr(slots, kb_off, bases, lw & 0x7FF);
+                        int coef = (int)((lw >> 11) & 31);
+                        if (coef >= 16) coef -= 32;
+                        uint32_t m = (lw >> 16) & 15;
+                        if (coef < 0) m ^= VM_NEG;
+                        const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+                        E1 x0, x1;
+                        if (C::LAZY_MODS) {
+                            load1(x0, px);
+                            load1(x1, px + N);
+                            if (m) lazy_mods(x0, x1, m);
+                        } else {
+                            E2 x;
+                            load2(x, px);
+                            if (m & ~VM_NEG) apply_mod(x, m & ~VM_NEG);
+                            x0 = x.c0; x1 = x.c1;
+                            if (m & VM_NEG) { p_minus_c(x0); p_minus_c(x1); }
+                        }
+                        if (mag != 1) { small_multiple_nr(x0, mag); small_multiple_nr(x1, mag); }
+                        wide_add_high(T0, x0);
+                        wide_add_high(T2, x1);
+                    }
+                }
                 const uint32_t levels = (hdr >> 18) & 3;
-                redc(res.c0, RE, levels);
+                redc(res.c0, T0, levels);
                 redc(res.c1, T2, levels);
             }
-            if (scale != 1) { mul_small(res.c0, res.c0, scale); mul_small(res.c1, res.c1, scale); }
+            if (!folded && scale != 1) { mul_small(res.c0, res.c0, scale); mul_small(res.c1, res.c1, scale); }
         } else {
             T::f2_zero(res);
         }
-        for (uint32_t t = 0; t < nl; t++) {
-            const uint32_t lw = w[8 + t];
-            E2 x;
-            load2(x, operand_ptr(c, lw & 0x7FF));
-            apply_mod(x, (lw >> 16) & 15);
-            int coef = (int)((lw >> 11) & 31);
-            if (coef >= 16) coef -= 32;
-            const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
-            if (mag != 1) { mul_small(x.c0, x.c0, mag); mul_small(x.c1, x.c1, mag); }
-            if (coef < 0) T::f2_sub(res, res, x); else T::f2_add(res, res, x);
+        if (!folded) {
+            for (uint32_t t = 0; t < nl; t++) {
+                const uint32_t lw = w[8 + t];
+                E2 x;
+                load2(x, slot_ptr(slots, kb_off, bases, lw & 0x7FF));
+                apply_mod(x, (lw >> 16) & 15);
+                int coef = (int)((lw >> 11) & 31);
+                if (coef >= 16) coef -= 32;
+                const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+                if (mag != 1) { mul_small(x.c0, x.c0, mag); mul_small(x.c1, x.c1, mag); }
+                if (coef < 0) T::f2_sub(res, res, x); else T::f2_add(res, res, x);
+            }
         }
         if (halve) T::f2_halve(res, res);
         store2(dst, res);

@@ -61,8 +61,8 @@ def operand_bounds(am):
     return b0, b1
 
 
-def dot_bounds(terms):
-    """(off, levels) of a dot product; terms = [(a, am, b, bm)]"""
+def _dot_k(terms):
+    """(off, k): offset index and the bound k of the reduction input in units of p^2; terms = [(a, am, b, bm)]"""
     p, R = _field['p'], 1 << (32 * _field['limbs'])
     ab = -_field['beta']
     off = kre = kim = ksum = 0
@@ -75,12 +75,50 @@ def dot_bounds(terms):
         ksum += (a0 + a1) * (b0 + b1)
     assert off <= 30, "offset table of k p^2 ends at k = 30"
     assert ksum * p * p < R * R, "T2 overflows 2N words"
-    k = max(off + kre, kim)                       # redc input < k p^2
+    return off, max(off + kre, kim)                       # redc input < k p^2
+
+
+def dot_bounds(terms):
+    """(off, levels) of a dot product; terms = [(a, am, b, bm)]"""
+    p, R = _field['p'], 1 << (32 * _field['limbs'])
+    off, k = _dot_k(terms)
     for levels in (1, 2, 3):
         # result < k p^2 / R + p  <  2^levels p   <=>   k p < (2^levels - 1) R
         if k * p < ((1 << levels) - 1) * R and (1 << levels) * p <= R:
             return off, levels
     raise AssertionError("dot product too wide for the field's head room: k = %d" % k)
+
+
+FOLD_SCALES = (1, 2, 3, 4, 6)
+
+
+def fold_bounds(v):
+    """Can the scale and the linear tail of DOT `v` be applied to the wide values BEFORE the reduction (csrc/vm.cuh exec_op:
+    scale * V, then  + |c| * mod(x) * R  into the high half)?  Returns the `levels` this needs, or None if the head room of
+    the field does not allow it.  Reduction input  s k p^2 + L p R  with L = sum |c_i| bound(mod(x_i)); the result is below
+    (s k p / R + L + 1) p."""
+    if v.scale == 1 and not v.lin:
+        return None
+    p, R = _field['p'], 1 << (32 * _field['limbs'])
+    _, k = _dot_k(v.terms)
+    s = v.scale
+    if s not in FOLD_SCALES:
+        return None
+    lin = 0
+    for (_, c, m) in v.lin:
+        mag = abs(c)
+        if mag > 4:
+            return None
+        mb = max(operand_bounds(m))
+        if mag * mb * p >= R:
+            return None
+        lin += mag * mb
+    if s * k * p * p + lin * p * R >= R * R:
+        return None
+    for levels in (1, 2, 3):
+        if s * k * p + (lin + 1) * R <= (1 << levels) * R and (1 << levels) * p <= R:
+            return levels
+    return None
 
 
 OP_WORDS = 12            # header + 6 terms + 4 lin + 1 spare  (fixed size keeps the interpreter trivial)
@@ -316,7 +354,8 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
         # the widest dot product of the phase: every lane runs the same multi-operand product variant (zero padded),
         # so lanes with fewer terms do not serialise against the others
         pmax = max([len(v.terms) for v in vs if v.kind == 'dot'] + [0])
-        levels = max([dot_bounds(v.terms)[1] for v in vs if v.kind == 'dot'] + [1])
+        fold = {id(v): fold_bounds(v) for v in vs if v.kind == 'dot'}
+        levels = max([fold[id(v)] or dot_bounds(v.terms)[1] for v in vs if v.kind == 'dot'] + [1])
         for v in lanes:
             w = [0] * OP_WORDS
             if v is not None:
@@ -327,7 +366,8 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
                 assert 1 <= v.scale <= 7
                 off = dot_bounds(v.terms)[0] if v.kind == 'dot' else 0
                 w[0] = (k | (nt << 4) | (nl << 8) | (v.scale << 12) | ((1 if v.halve else 0) << 15) | (v.pred << 16) |
-                        (levels << 18) | (pmax << 20) | (off << 24))
+                        (levels << 18) | (pmax << 20) | (off << 24) |
+                        ((1 if v.kind == 'dot' and fold[id(v)] else 0) << 29))
                 w[1] = enc_operand(loc(v)) | (alt << 16)
                 for t, (a, am, b, bm) in enumerate(v.terms):
                     w[2 + t] = enc_operand(loc(a)) | (enc_operand(loc(b)) << 11) | (am << 22) | (bm << 26)

@@ -59,7 +59,7 @@ class Curve:
 # name -> (p, 32-bit limbs, u^2, lazy operand modifiers)
 FIELDS = {
     'BN254': (0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47, 8, -1, False),
-    'BLS381': (0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab, 12, -1, False),
+    'BLS381': (0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab, 12, -1, True),
     'BLS377': (0x01ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001, 12, -5, False),
 }
 
@@ -466,8 +466,9 @@ def build_all(curve_name):
     cv = CURVES[curve_name]
     _cfg['nslots'], _cfg['nregs'] = SLOTCFG[curve_name]
     _cfg['qstride'] = 3 if cv.family == 'bn' else 2
-    # field parameters for the lazy-reduction bounds (compiler.dot_bounds).  The interpreter's operand modifiers are
-    # canonical on every curve (lazy = False); the unreduced variant measured slower
+    # field parameters for the lazy-reduction bounds (compiler.dot_bounds).  BLS12-381 (xi = 1 + u, three spare bits above p)
+    # runs the interpreter's unreduced operand modifiers (csrc/vm.cuh lazy_mods, curves.cuh LAZY_MODS); the other two curves
+    # keep canonical modifiers
     set_field(*FIELDS[curve_name])
     progs = {}
     for np_ in (1, 2):

@@ -26,6 +26,7 @@ struct CurveConsts {
     uint32_t ts_exp[N];      // Tonelli-Shanks: (q-1)/2 with p-1 = 2^s q
     uint32_t ts_z[N];        // g^q for a quadratic non-residue g (Montgomery)
     uint32_t half_p[N];      // (p-1)/2: y is "lexicographically largest" iff y > half_p
+    uint32_t pk[2 * N];      // 2p, 4p
 };
 
 #define B200_DEFINE_CONSTS(NAME, NL)                                                        \
@@ -33,7 +34,7 @@ struct CurveConsts {
                                              NAME##_B3, NAME##_BTW, NAME##_ORDER,           \
                                              NAME##_FROB1, NAME##_FROB2, NAME##_FROB3, NAME##_P2, \
                                              NAME##_R3, NAME##_GLV_LAMBDA, NAME##_GLV_M,    \
-                                             NAME##_GLV_BETA, NAME##_TS_EXP, NAME##_TS_Z, NAME##_HALF_P};
+                                             NAME##_GLV_BETA, NAME##_TS_EXP, NAME##_TS_Z, NAME##_HALF_P, NAME##_PK};
 
 B200_DEFINE_CONSTS(BN254, 8)
 B200_DEFINE_CONSTS(BLS381, 12)
@@ -47,7 +48,7 @@ B200_DEFINE_CONSTS(BLS377, 12)
                                                         NAME##_FROB2, NAME##_FROB3, NAME##_P2,      \
                                                         NAME##_R3, NAME##_GLV_LAMBDA,       \
                                                         NAME##_GLV_M, NAME##_GLV_BETA,      \
-                                                        NAME##_TS_EXP, NAME##_TS_Z, NAME##_HALF_P};
+                                                        NAME##_TS_EXP, NAME##_TS_Z, NAME##_HALF_P, NAME##_PK};
 B200_DEFINE_DCONSTS(BN254, 8)
 B200_DEFINE_DCONSTS(BLS381, 12)
 B200_DEFINE_DCONSTS(BLS377, 12)

@@ -251,6 +251,9 @@ def main():
             p2 += limbs((k * p * p) % (1 << (64 * n)), 2 * n)
         out.append('#define %s_P2 %s' % (name, fmt(p2)))
         out.append('#define %s_R3 %s' % (name, fmt(limbs(pow(R, 3, p), n))))
+        # 2p and 4p (vm.cuh: conditional subtractions that canonicalise a lazily reduced result)
+        assert 4 * p < (1 << (32 * n))
+        out.append('#define %s_PK %s' % (name, fmt(limbs(2 * p, n) + limbs(4 * p, n))))
         # GLV (g1.cuh): lambda (4 words), M = floor(2^256 / lambda) (5 words), beta (Montgomery); zeros = no GLV (BN254)
         if c['fam'] == 'bls12':
             lam, gbeta = glv_params(p, r, c['x'], c['b'])

@@ -228,10 +228,17 @@ struct Vm {
         if (m & VM_NEG) p_minus(a0, a0);
         if (((m & VM_NEG) != 0) != ((m & VM_CONJ) != 0)) p_minus(a1, a1);
         if (m & VM_XI) {
-            E1 s, d;
+            E1 s;
             add_nr(s, a0, a1);
-            p_minus(d, a1);
-            add_nr(a0, a0, d);
+            const uint32_t* p = C::p();                 // (a0 + p) - a1: two plain chains, no complement of a1 needed
+            a0.l[0] = add_cc(a0.l[0], p[0]);
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) a0.l[i] = addc_cc(a0.l[i], p[i]);
+            a0.l[N - 1] = addc(a0.l[N - 1], p[N - 1]);
+            a0.l[0] = sub_cc(a0.l[0], a1.l[0]);
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) a0.l[i] = subc_cc(a0.l[i], a1.l[i]);
+            a0.l[N - 1] = subc(a0.l[N - 1], a1.l[N - 1]);
             a1 = s;
         }
         if (m & VM_DBL) { shl1(a0); shl1(a1); }
@@ -328,17 +335,13 @@ struct Vm {
         acc[N] = addc_cc(acc[N], 0);
         acc[N + 1] = addc(acc[N + 1], 0);
     }
-    // r -= (p << sh) if r >= (p << sh)
+    // r -= (p << sh) if r >= (p << sh), sh = 0, 1, 2 (2p and 4p come from the constant table)
     static B200_HD void cond_sub_kp(E1& r, int sh) {
-        const uint32_t* p = C::p();
+        const uint32_t* q = sh == 0 ? C::p() : C::K().pk + (sh - 1) * N;
         uint32_t t[N];
-        uint32_t q0 = p[0] << sh;
-        t[0] = sub_cc(r.l[0], q0);
+        t[0] = sub_cc(r.l[0], q[0]);
 #pragma unroll
-        for (int i = 1; i < N; i++) {
-            uint32_t qi = sh ? ((p[i] << sh) | (p[i - 1] >> (32 - sh))) : p[i];
-            t[i] = subc_cc(r.l[i], qi);
-        }
+        for (int i = 1; i < N; i++) t[i] = subc_cc(r.l[i], q[i]);
         uint32_t borrow = subc(0, 0);
 #pragma unroll
         for (int i = 0; i < N; i++) r.l[i] = borrow ? r.l[i] : t[i];

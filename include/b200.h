@@ -163,6 +163,13 @@ int b200_g2_compress_batch(int curve, size_t n, const void* pts, void* compresse
 int b200_g1_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 int b200_g2_validate_batch(int curve, size_t n, const void* pts, void* ok_out, uint32_t flags);
 
+/* G2 MultiScalarMul: out = sum_i [k_i] Q_i on the twist E'(Fp2) -- the G2 counterpart of driver.Curve.MultiScalarMul
+   (reference driver/math.go:170) built from driver.G2.Mul / driver.G2.Add (reference driver/math.go:307-310; gnark
+   G2Affine.MultiExp is what a gurvy-style adapter would forward to).  n G2 elements (G2.Bytes() layout, or MONT with
+   B200_IN_MONT) and n 32-byte big-endian scalars -> one G2 element.  Same Pippenger pipeline as b200_g1_msm with the
+   XYZZ formulas over Fp2; one device per call (combine per-GPU partial sums with b200_g2_sum_batch-style addition). */
+int b200_g2_msm(int curve, size_t n, const void* pts, const void* scalars, void* out, uint32_t flags);
+
 /* Batch affine normalisation (Montgomery's trick, one inversion per 8 points): n Jacobian G1 points given as MONT limbs
    X | Y | Z (kilic PointG1 [3]fe, reference driver/kilic/bls12-381.go:20-23; gnark G1Jac) -> n affine G1 elements
    (X / Z^2, Y / Z^3) in BYTES form (what G1.Bytes() returns, reference kilic/bls12-381.go:74-78) or MONT with

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "b200_pairing_fixed_batch": (_int, [_u64, _sz, _vp, _vp, _vp, _u32]),
     "b200_pairing2_fixed_batch": (_int, [_u64, _sz, _vp, _vp, _vp, _vp, _vp, _u32]),
     "b200_g1_normalize_batch": (_int, [_int, _sz, _vp, _vp, _u32]),
+    "b200_g2_msm": (_int, [_int, _sz, _vp, _vp, _vp, _u32]),
     "b200_hash_to_g1_batch": (_int, [_int, _sz, _vp, _vp, _vp, _sz, _vp, _u32]),
     "b200_launch_count": (_u64, []),
 }

@@ -226,11 +226,13 @@ uint64_t g_next_handle = 1;
 
 // carve the MSM workspace; returns bytes needed (buf may be null to size only)
 size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_points, uint8_t* base, MsmBuffers* b,
-                 uint8_t** scalars_dev, uint8_t** pts_in_dev, size_t pts_in_bytes, uint8_t** out_dev) {
+                 uint8_t** scalars_dev, uint8_t** pts_in_dev, size_t pts_in_bytes, uint8_t** out_dev, size_t gmul = 1) {
+    // gmul = 1: G1 (coordinates in Fp), 2: G2 (coordinates in Fp2: twice the bytes per point)
+    const size_t aff_size = vt->aff_size * gmul, xyzz_size = vt->xyzz_size * gmul;
     size_t off = 0;
     auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
     size_t nb = (size_t)pl.W * pl.B;
-    b->points = need_points ? take(n * vt->aff_size) : nullptr;
+    b->points = need_points ? take(n * aff_size) : nullptr;
     b->digits = (uint32_t*)take((size_t)pl.W * n * 4);
     b->sorted = (uint32_t*)take((size_t)pl.W * n * 4);
     b->counts = (uint32_t*)take(nb * 4);
@@ -238,25 +240,26 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
     b->cursor = (uint32_t*)take(nb * 4);
     b->perm = (uint32_t*)take(nb * 4);
     b->size_hist = (uint32_t*)take(2 * 1024 * 4);
-    b->buckets = take(nb * vt->xyzz_size);
-    b->chunks = take((size_t)pl.W * pl.nchunks * vt->xyzz_size);
-    b->windows = take((size_t)pl.W * 9 * vt->xyzz_size);      // W window sums + 8 partial sums per window
+    b->buckets = take(nb * xyzz_size);
+    b->chunks = take((size_t)pl.W * pl.nchunks * xyzz_size);
+    b->windows = take((size_t)pl.W * 9 * xyzz_size);      // W window sums + 8 partial sums per window
     b->max_heavy = (uint32_t)(((size_t)pl.W * n) / 512);       // B200_MSM_SEG = 512 points per segment
     b->heavy_n = (uint32_t*)take(4);
     b->heavy_items = take((size_t)b->max_heavy * 8);
-    b->heavy_partial = take((size_t)b->max_heavy * vt->xyzz_size);
+    b->heavy_partial = take((size_t)b->max_heavy * xyzz_size);
     if (scalars_dev) *scalars_dev = take(n * 32);
     if (pts_in_dev) *pts_in_dev = take(pts_in_bytes);
-    if (out_dev) *out_dev = take(2 * (size_t)vt->fp_bytes);
+    if (out_dev) *out_dev = take(2 * (size_t)vt->fp_bytes * gmul);
     return off;
 }
 
 // MSM of host points/scalars [lo,hi) on one device -> one affine point written to out_host
 int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const void* pts, const void* resident_pts,
-                   const void* scalars, void* out_host, uint32_t flags, const Bases* bs = nullptr) {
+                   const void* scalars, void* out_host, uint32_t flags, const Bases* bs = nullptr, bool g2 = false) {
     const CurveVTable* vt = ci.vt;
     size_t m = hi - lo;
-    size_t g1sz = 2 * (size_t)vt->fp_bytes;
+    const size_t gmul = g2 ? 2 : 1;
+    size_t g1sz = 2 * (size_t)vt->fp_bytes * gmul;           // bytes of one point on the wire (G1 or G2)
     WsGuard g(dev);
     if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
     Workspace& w = *g.w;
@@ -265,22 +268,22 @@ int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const voi
     MsmBuffers b;
     uint8_t *d_sc = nullptr, *d_pin = nullptr, *d_out = nullptr;
     bool need_points = resident_pts == nullptr;
-    size_t need = msm_carve(vt, pl, m, need_points, nullptr, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out);
+    size_t need = msm_carve(vt, pl, m, need_points, nullptr, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out, gmul);
     if (int rc = w.reserve(need)) return rc;
-    msm_carve(vt, pl, m, need_points, w.buf, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out);
+    msm_carve(vt, pl, m, need_points, w.buf, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out, gmul);
     CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
     const void* prepared = resident_pts;
     if (m) {
         CU(cudaMemcpyAsync(d_sc, (const uint8_t*)scalars + lo * 32, m * 32, cudaMemcpyHostToDevice, w.stream));
         if (need_points) {
             CU(cudaMemcpyAsync(d_pin, (const uint8_t*)pts + lo * g1sz, m * g1sz, cudaMemcpyHostToDevice, w.stream));
-            CU(vt->msm_points(m, d_pin, b.points, kernel_flags(flags), w.d_err, w.stream));
+            CU((g2 ? vt->msm_points_g2 : vt->msm_points)(m, d_pin, b.points, kernel_flags(flags), w.d_err, w.stream));
             prepared = b.points;
         } else {
             prepared = (const uint8_t*)resident_pts + lo * vt->aff_size;
         }
     }
-    CU(vt->msm(m, prepared, d_sc, d_out, kernel_flags(flags), pl, b, w.stream));
+    CU((g2 ? vt->msm_g2 : vt->msm)(m, prepared, d_sc, d_out, kernel_flags(flags), pl, b, w.stream));
     int h_err = 0;
     CU(cudaMemcpyAsync(out_host, d_out, g1sz, cudaMemcpyDeviceToHost, w.stream));
     CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
@@ -524,7 +527,7 @@ int b200_g1_sum(int curve, size_t n, const void* pts, void* out, uint32_t flags)
 }
 
 static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool prepared, const void* scalars,
-                           void* out, uint32_t flags, const Bases* bs = nullptr) {
+                           void* out, uint32_t flags, const Bases* bs = nullptr, bool g2 = false) {
     // device-pointer MSM: the call returns while its kernels are still queued, so the scratch slab cannot go back to
     // the pool at return.  It is kept per (calling thread, device, stream) -- two streams never share a slab, MSMs
     // issued on one stream are ordered by the stream -- and returned to the pool, after draining the stream, when the
@@ -550,19 +553,31 @@ static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool 
     MsmPlan pl = resident_plan(vt, bs, n);
     MsmBuffers b;
     bool need_points = !prepared;
-    size_t need = msm_carve(vt, pl, n, need_points, nullptr, &b, nullptr, nullptr, 0, nullptr);
+    const size_t gmul = g2 ? 2 : 1;
+    size_t need = msm_carve(vt, pl, n, need_points, nullptr, &b, nullptr, nullptr, 0, nullptr, gmul);
     if (need > w->cap) {
         CU(cudaStreamSynchronize(t_stream));     // earlier async work may still use the old slab
         if (int rc = w->reserve(need)) return rc;
     }
-    msm_carve(vt, pl, n, need_points, w->buf, &b, nullptr, nullptr, 0, nullptr);
+    msm_carve(vt, pl, n, need_points, w->buf, &b, nullptr, nullptr, 0, nullptr, gmul);
     const void* prep = pts;
     if (need_points && n) {
-        CU(vt->msm_points(n, (const uint8_t*)pts, b.points, kernel_flags(flags), device_err_flag(dev), t_stream));
+        CU((g2 ? vt->msm_points_g2 : vt->msm_points)(n, (const uint8_t*)pts, b.points, kernel_flags(flags), device_err_flag(dev), t_stream));
         prep = b.points;
     }
-    CU(vt->msm(n, prep, (const uint8_t*)scalars, (uint8_t*)out, kernel_flags(flags), pl, b, t_stream));
+    CU((g2 ? vt->msm_g2 : vt->msm)(n, prep, (const uint8_t*)scalars, (uint8_t*)out, kernel_flags(flags), pl, b, t_stream));
     return 0;
+}
+
+// G2 MSM: sum_i [k_i] Q_i over E'(Fp2).  One device per call: the caller shards ranges and combines the
+// partial sums with b200_g2_sum, exactly as for G1.
+int b200_g2_msm(int curve, size_t n, const void* pts, const void* scalars, void* out, uint32_t flags) {
+    if (int rc = ensure_init()) return rc;
+    CurveInfo ci;
+    if (!curve_info(curve, &ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out || (n && (!pts || !scalars))) return fail(B200_ERR_ARG, "null buffer");
+    if (flags & B200_DEVICE_PTRS) return msm_device_ptrs(ci, n, pts, false, scalars, out, flags, nullptr, true);
+    return msm_host_range(ci, current_device(), 0, n, pts, nullptr, scalars, out, flags, nullptr, true);
 }
 
 int b200_g1_msm(int curve, size_t n, const void* pts, const void* scalars, void* out, uint32_t flags) {

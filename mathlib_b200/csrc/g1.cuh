@@ -39,6 +39,7 @@ struct G1Ops {
         p.x = a.x; p.y = a.y; F::one(p.zz); F::one(p.zzz);
     }
     static B200_HD void neg_affine(Aff& r, const Aff& a) { r.x = a.x; F::neg(r.y, a.y); }
+    static B200_HD void neg_y(Aff& a) { F::neg(a.y, a.y); }                    // group-generic MSM kernels (msm.cuh)
     static B200_HD void neg(Pt& r, const Pt& a) { r.x = a.x; F::neg(r.y, a.y); r.zz = a.zz; r.zzz = a.zzz; }
 
     // p <- 2a for affine a (mdbl-2008-s-1)

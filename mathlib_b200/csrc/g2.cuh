@@ -94,6 +94,37 @@ struct G2Ops {
         T::f2_mul(p.zz, p.zz, PP);
         T::f2_mul(p.zzz, p.zzz, PPP);
     }
+    static B200_HD void neg_y(Aff& a) { T::f2_neg(a.y, a.y); }
+    // p <- p + q (add-2008-s), complete: the bucket sums of the G2 MSM (msm.cuh)
+    static B200_HD_NOINLINE void add(Pt& p, const Pt& q) {
+        if (is_inf(q)) return;
+        if (is_inf(p)) { p = q; return; }
+        E U1, U2, S1, S2, Pp, R, PP, PPP, Q, t;
+        T::f2_mul(U1, p.x, q.zz);
+        T::f2_mul(U2, q.x, p.zz);
+        T::f2_mul(S1, p.y, q.zzz);
+        T::f2_mul(S2, q.y, p.zzz);
+        T::f2_sub(Pp, U2, U1);
+        T::f2_sub(R, S2, S1);
+        if (T::f2_is_zero(Pp)) {
+            if (T::f2_is_zero(R)) dbl(p); else set_inf(p);
+            return;
+        }
+        T::f2_sqr(PP, Pp);
+        T::f2_mul(PPP, Pp, PP);
+        T::f2_mul(Q, U1, PP);
+        T::f2_sqr(t, R);
+        T::f2_sub(t, t, PPP); T::f2_sub(t, t, Q); T::f2_sub(t, t, Q);   // X3
+        T::f2_sub(Q, Q, t);
+        T::f2_mul(Q, R, Q);
+        T::f2_mul(S1, S1, PPP);
+        T::f2_sub(p.y, Q, S1);
+        p.x = t;
+        T::f2_mul(p.zz, p.zz, q.zz);
+        T::f2_mul(p.zz, p.zz, PP);
+        T::f2_mul(p.zzz, p.zzz, q.zzz);
+        T::f2_mul(p.zzz, p.zzz, PPP);
+    }
     // affine (x,y) = (X/ZZ, Y/ZZZ); infinity -> (0,0)
     static B200_HD void to_affine(Aff& a, const Pt& p) {
         if (is_inf(p)) { T::f2_zero(a.x); T::f2_zero(a.y); return; }

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include "msm.cuh"
 #include "pairing_vm.cuh"
 #include "g2.cuh"
@@ -78,6 +79,10 @@ struct CurveVTable {
     // MSM over prepared points
     cudaError_t (*msm)(size_t n, const void* prepared_pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
                        const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s);
+    // G2 MSM: BYTES -> Montgomery affine G2 points, then the same pipeline over Fp2
+    cudaError_t (*msm_points_g2)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
+    cudaError_t (*msm_g2)(size_t n, const void* prepared_pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
+                          const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s);
 };
 
 const CurveVTable* vtable_bn254();
@@ -402,9 +407,13 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
-    static cudaError_t msm(size_t n, const void* pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
-                           const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s) {
-        typedef G1XYZZ<C::N> Pt;
+    // the Pippenger pipeline for G = G1Ops<C> (driver.Curve.MultiScalarMul) or G2Ops<C> (G2 MSM)
+    template <class G>
+    static cudaError_t msm_impl(size_t n, const void* pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
+                                const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s) {
+        typedef typename G::Pt Pt;
+        typedef typename G::Aff Aff;
+        constexpr bool IS_G1 = std::is_same<G, G1Ops<C>>::value;
         size_t nb = (size_t)pl.W * pl.B;
         cudaError_t e;
         if ((e = cudaMemsetAsync(b.counts, 0, nb * sizeof(uint32_t), s)) != cudaSuccess) return e;
@@ -432,46 +441,63 @@ struct Launch {
                                                                       b.max_heavy);
             B200_COUNT_LAUNCH();
         }
-        msm_accumulate_kernel<C><<<blocks_for(nb, 128), 128, 0, s>>>(n, pl, (const G1Affine<C::N>*)pts, b.offsets,
+        msm_accumulate_kernel<C, G, (IS_G1 ? B200_MSM_ACC_MIN_BLOCKS : 2)><<<blocks_for(nb, 128), 128, 0, s>>>(n, pl, (const Aff*)pts, b.offsets,
                                                                     b.counts, b.sorted, b.perm, (Pt*)b.buckets);
         B200_COUNT_LAUNCH();
         if (b.max_heavy) {
             // long runs (more than B200_MSM_SEG points in one bucket): split over extra threads; empty for uniform scalars
             const unsigned hb = blocks_for(b.max_heavy, 128);
-            msm_heavy_accumulate_kernel<C><<<hb, 128, 0, s>>>(n, pl, (const G1Affine<C::N>*)pts, b.offsets, b.counts, b.sorted,
+            msm_heavy_accumulate_kernel<C, G><<<hb, 128, 0, s>>>(n, pl, (const Aff*)pts, b.offsets, b.counts, b.sorted,
                                                               b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
                                                               (Pt*)b.heavy_partial);
-            msm_heavy_merge_kernel<C><<<hb, 128, 0, s>>>(b.counts, b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
+            msm_heavy_merge_kernel<C, G><<<hb, 128, 0, s>>>(b.counts, b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
                                                          (const Pt*)b.heavy_partial, (Pt*)b.buckets);
             B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
         }
         MsmPlan pt = pl;                             // plan of the tail (one window when the bucket arrays were folded)
-        if (pl.tables && pl.W > 1) {
-            msm_fold_kernel<C><<<blocks_for(pl.B, 128), 128, 0, s>>>(pl, (Pt*)b.buckets);
-            B200_COUNT_LAUNCH();
-            pt.W = 1;
+        if constexpr (IS_G1) {
+            if (pl.tables && pl.W > 1) {
+                msm_fold_kernel<C><<<blocks_for(pl.B, 128), 128, 0, s>>>(pl, (Pt*)b.buckets);
+                B200_COUNT_LAUNCH();
+                pt.W = 1;
+            }
         }
-        msm_reduce_kernel<C><<<blocks_for((size_t)pt.W * pt.nchunks, 128), 128, 0, s>>>(pt, (const Pt*)b.buckets,
+        msm_reduce_kernel<C, G><<<blocks_for((size_t)pt.W * pt.nchunks, 128), 128, 0, s>>>(pt, (const Pt*)b.buckets,
                                                                                         (Pt*)b.chunks);
         B200_COUNT_LAUNCH();
         if (pt.nchunks >= 1024) {
             // two stages: 8 partial sums per window (buffer behind the W window slots), then the windows
             Pt* part = (Pt*)b.windows + pl.W;
-            msm_window_sum_kernel<C><<<pt.W * 8, 64, 64 * sizeof(Pt), s>>>(pt.nchunks / 8, (const Pt*)b.chunks, part);
-            msm_window_sum_kernel<C><<<pt.W, 32, 32 * sizeof(Pt), s>>>(8, (const Pt*)part, (Pt*)b.windows);
+            msm_window_sum_kernel<C, G><<<pt.W * 8, 64, 64 * sizeof(Pt), s>>>(pt.nchunks / 8, (const Pt*)b.chunks, part);
+            msm_window_sum_kernel<C, G><<<pt.W, 32, 32 * sizeof(Pt), s>>>(8, (const Pt*)part, (Pt*)b.windows);
             B200_COUNT_LAUNCH();
         } else {
-            msm_window_sum_kernel<C><<<pt.W, 64, 64 * sizeof(Pt), s>>>(pt.nchunks, (const Pt*)b.chunks, (Pt*)b.windows);
+            msm_window_sum_kernel<C, G><<<pt.W, 64, 64 * sizeof(Pt), s>>>(pt.nchunks, (const Pt*)b.chunks, (Pt*)b.windows);
         }
         B200_COUNT_LAUNCH();
-        msm_final_kernel<C><<<1, 32, 0, s>>>(pt, (const Pt*)b.windows, out, flags);
+        if constexpr (IS_G1) msm_final_kernel<C><<<1, 32, 0, s>>>(pt, (const Pt*)b.windows, out, flags);
+        else msm_final_g2_kernel<C><<<1, 32, 0, s>>>(pt, (const Pt*)b.windows, out, flags);
+        B200_COUNT_LAUNCH();
+        return cudaGetLastError();
+    }
+    static cudaError_t msm(size_t n, const void* pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
+                           const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s) {
+        return msm_impl<G1Ops<C>>(n, pts, scalars, out, flags, pl, b, s);
+    }
+    static cudaError_t msm_g2(size_t n, const void* pts, const uint8_t* scalars, uint8_t* out, uint32_t flags,
+                              const MsmPlan& pl, const MsmBuffers& b, cudaStream_t s) {
+        return msm_impl<G2Ops<C>>(n, pts, scalars, out, flags, pl, b, s);
+    }
+    static cudaError_t msm_points_g2(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        msm_points_g2_kernel<C><<<blocks_for(n, 128), 128, 0, s>>>(n, pts, (G2Aff<C::N>*)out, flags, err);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
                                       &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec, &g1_normalize,
-                                      (C::N == 12 && C::BETA == -1) ? &hash_to_g1 : nullptr, &msm_points, &msm_tables, &msm};
+                                      (C::N == 12 && C::BETA == -1) ? &hash_to_g1 : nullptr, &msm_points, &msm_tables, &msm, &msm_points_g2, &msm_g2};
         return &t;
     }
 };

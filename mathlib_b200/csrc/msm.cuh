@@ -19,6 +19,7 @@
 #pragma once
 #include <cstdlib>
 #include "kernels.cuh"
+#include "g2.cuh"
 
 namespace b200 {
 
@@ -225,13 +226,14 @@ static __global__ void msm_heavy_list_kernel(size_t nb, const uint32_t* counts, 
     const uint32_t pos = atomicAdd(heavy_n, k);
     for (uint32_t s = 1; s <= k && pos + s - 1 < max_items; s++) items[pos + s - 1] = {(uint32_t)t, s};
 }
-template <class C>
+// The bucket kernels below are generic in the group: G = G1Ops<C> (driver.Curve.MultiScalarMul) or G2Ops<C> (the G2 MSM,
+// SURVEY 8(f) row 3) -- same digits, sort and schedule, XYZZ formulas over Fp or Fp2.
+template <class C, class G = G1Ops<C>>
 __global__ void __launch_bounds__(128, 2)
-msm_heavy_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
-                            const uint32_t* sorted, const uint32_t* heavy_n, const MsmHeavyItem* items, G1XYZZ<C::N>* partial) {
+msm_heavy_accumulate_kernel(size_t n, MsmPlan pl, const typename G::Aff* pts, const uint32_t* offsets, const uint32_t* counts,
+                            const uint32_t* sorted, const uint32_t* heavy_n, const MsmHeavyItem* items, typename G::Pt* partial) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= *heavy_n) return;
-    typedef G1Ops<C> G;
     const MsmHeavyItem it = items[id];
     const size_t t = it.bucket, w = t / pl.B;
     if (pl.tables) pts += w * pl.stride;
@@ -244,21 +246,20 @@ msm_heavy_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, con
     for (uint32_t j = lo; j < hi; j++) {
         const uint32_t e = run[j];
         typename G::Aff a = pts[e >> 1];
-        if (e & 1) FpOps<C>::neg(a.y, a.y);
+        if (e & 1) G::neg_y(a);
         G::madd(acc, a);
     }
     partial[id] = acc;
 }
 // one thread per heavy bucket (the thread of its first item): the items of a bucket are contiguous in the list
-template <class C>
+template <class C, class G = G1Ops<C>>
 __global__ void __launch_bounds__(128, 2)
-msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const MsmHeavyItem* items, const G1XYZZ<C::N>* partial,
-                       G1XYZZ<C::N>* buckets) {
+msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const MsmHeavyItem* items, const typename G::Pt* partial,
+                       typename G::Pt* buckets) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= *heavy_n) return;
     const MsmHeavyItem it = items[id];
     if (it.seg != 1) return;
-    typedef G1Ops<C> G;
     const uint32_t k = (counts[it.bucket] - 1) / B200_MSM_SEG;
     typename G::Pt acc = buckets[it.bucket];
     for (uint32_t s = 0; s < k; s++) {
@@ -271,14 +272,13 @@ msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const Ms
 #ifndef B200_MSM_ACC_MIN_BLOCKS
 #define B200_MSM_ACC_MIN_BLOCKS 4      // measured at 2^20 points: 2 blocks (188 regs) 9.64 ms, 3 (168) 9.25 ms, 4 (128, a few spills) 9.17 ms
 #endif
-template <class C>
-__global__ void __launch_bounds__(128, B200_MSM_ACC_MIN_BLOCKS)
-msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uint32_t* offsets, const uint32_t* counts,
-                      const uint32_t* sorted, const uint32_t* perm, G1XYZZ<C::N>* buckets) {
+template <class C, class G = G1Ops<C>, int MINB = B200_MSM_ACC_MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MINB)
+msm_accumulate_kernel(size_t n, MsmPlan pl, const typename G::Aff* pts, const uint32_t* offsets, const uint32_t* counts,
+                      const uint32_t* sorted, const uint32_t* perm, typename G::Pt* buckets) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)pl.W * pl.B) return;
     const size_t t = perm[tid];
-    typedef G1Ops<C> G;
     size_t w = t / pl.B;
     if (pl.tables) pts += w * pl.stride;
     const uint32_t* run = sorted + w * n + offsets[t];
@@ -295,7 +295,7 @@ msm_accumulate_kernel(size_t n, MsmPlan pl, const G1Affine<C::N>* pts, const uin
         typename G::Aff a = nxt;
         const uint32_t e = e_nxt;
         if (j + 1 < cnt) { e_nxt = run[j + 1]; nxt = pts[e_nxt >> 1]; }
-        if (e & 1) FpOps<C>::neg(a.y, a.y);
+        if (e & 1) G::neg_y(a);
         G::madd(acc, a);
     }
     buckets[t] = acc;
@@ -335,14 +335,13 @@ msm_fold_kernel(MsmPlan pl, G1XYZZ<C::N>* buckets) {
 }
 
 // thread (w, chunk t): G = sum_{j=1..S} (t*S + j) * B[w][t*S + j - 1]
-template <class C>
+template <class C, class G = G1Ops<C>>
 __global__ void __launch_bounds__(128)
-msm_reduce_kernel(MsmPlan pl, const G1XYZZ<C::N>* buckets, G1XYZZ<C::N>* chunk_out) {
+msm_reduce_kernel(MsmPlan pl, const typename G::Pt* buckets, typename G::Pt* chunk_out) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= (size_t)pl.W * pl.nchunks) return;
-    typedef G1Ops<C> G;
     size_t w = id / pl.nchunks, t = id % pl.nchunks;
-    const G1XYZZ<C::N>* b = buckets + w * pl.B + t * pl.chunk;
+    const typename G::Pt* b = buckets + w * pl.B + t * pl.chunk;
     typename G::Pt run, acc;
     G::set_inf(run);
     G::set_inf(acc);
@@ -368,10 +367,9 @@ msm_reduce_kernel(MsmPlan pl, const G1XYZZ<C::N>* buckets, G1XYZZ<C::N>* chunk_o
 // segment sums: out[seg] = sum of in[seg*count .. seg*count + count), one block per segment (shared-memory tree).
 // The per-window sum of the chunk results runs in two stages (W*8 segments, then W) so that it spreads over 128 SMs
 // instead of 16.
-template <class C>
-__global__ void msm_window_sum_kernel(int count, const G1XYZZ<C::N>* in, G1XYZZ<C::N>* out) {
+template <class C, class G = G1Ops<C>>
+__global__ void msm_window_sum_kernel(int count, const typename G::Pt* in, typename G::Pt* out) {
     extern __shared__ uint32_t shraw[];
-    typedef G1Ops<C> G;
     typename G::Pt* sh = reinterpret_cast<typename G::Pt*>(shraw);
     const size_t seg = blockIdx.x;
     typename G::Pt acc;
@@ -503,6 +501,35 @@ __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_
     typename G::Aff r;
     G::to_affine(r, acc);
     if (lane == 0) Codec<C>::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);
+}
+
+// ---- G2 MSM: the same pipeline over E'(Fp2).  Points: reference G2.Bytes() encodings (or Montgomery
+// slabs) -> Montgomery affine; tail: Horner over the windows in XYZZ on one thread (not latency-tuned like the G1 tail).
+template <class C>
+__global__ void msm_points_g2_kernel(size_t n, const uint8_t* pts, G2Aff<C::N>* out, uint32_t flags, int* err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int e = 0;
+    G2Aff<C::N> a;
+    Codec<C>::g2_load(a, pts + i * Codec<C>::g2_size(), flags & FLAG_IN_MONT, &e);
+    if (e) atomicExch(err, 1);
+    out[i] = a;
+}
+template <class C>
+__global__ void msm_final_g2_kernel(MsmPlan pl, const G2XYZZ<C::N>* windows, uint8_t* out, uint32_t flags) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    typedef G2Ops<C> G;
+    typename G::Pt acc;
+    G::set_inf(acc);
+    for (int w = pl.W - 1; w >= 0; w--) {
+        if (!G::is_inf(acc))
+            for (int k = 0; k < msm_win_width(pl, w); k++) G::dbl(acc);
+        typename G::Pt v = windows[w];
+        G::add(acc, v);
+    }
+    typename G::Aff r;
+    G::to_affine(r, acc);
+    G2Codec<C>::g2_store(out, r, flags & FLAG_OUT_MONT);
 }
 
 #endif  // __CUDACC__

@@ -35,13 +35,6 @@ struct Vm {
         uint32_t live;              // bit k: pair k is live
     };
 
-    static B200_HD const uint32_t* operand_ptr(const Ctx& c, uint32_t o) {
-        uint32_t cls = (o >> 8) & 7, idx = o & 255;
-        if (cls == VM_C_CONST) return c.kbank + idx * SLOT_WORDS;
-        // no dynamic indexing of base[] (it would force the context into local memory)
-        uint32_t b = cls == VM_C_ABS ? 0u : (cls == VM_C_B1 ? c.base[0] : (cls == VM_C_B2 ? c.base[1] : c.base[2]));
-        return c.slots + (b + idx) * SLOT_WORDS;
-    }
     // slots are 16-byte aligned (slot = 2N words, N a multiple of 4): 128-bit accesses
     struct alignas(16) Q4 { uint32_t x, y, z, w; };
     static B200_HD void load2(E2& r, const uint32_t* p) {
@@ -73,73 +66,16 @@ struct Vm {
     // ---------------------------------------------------------------------------------------------------
     // wide arithmetic
     // ---------------------------------------------------------------------------------------------------
-    static constexpr int AW = 2 * N + 2;         // words of an even / odd accumulator array
-    // v[0..2N) = a * b, unreduced.  Operand scanning with the products split by the parity of their word position:
-    // a[j]*b[i] lands on word i+j; even positions accumulate in Ev, odd ones in Od (Od[k] holds word k+1).  Every
-    // 32x32 product is one IMAD.WIDE.U32.X inside a carry chain (two independent chains per row) -- one instruction
-    // per multiply-accumulate, against two for a product-scanning column sum.  The two halves are merged at the end.
-    static B200_HD void wide_mul(uint32_t* v, const uint32_t* a, const uint32_t* b) {
-        uint32_t Ev[2 * N + 1], Od[2 * N];
-        // row 0: plain products
-#pragma unroll
-        for (int j = 0; j < N; j += 2) {
-            Ev[j] = mul_lo(a[j], b[0]);
-            Ev[j + 1] = mul_hi(a[j], b[0]);
-            Od[j] = mul_lo(a[j + 1], b[0]);
-            Od[j + 1] = mul_hi(a[j + 1], b[0]);
-        }
-#pragma unroll
-        for (int k = N; k < 2 * N + 1; k++) Ev[k] = 0;
-#pragma unroll
-        for (int k = N; k < 2 * N; k++) Od[k] = 0;
-#pragma unroll
-        for (int i = 1; i < N; i++) {
-            const int je = i & 1;          // first j with (i+j) even
-            const int jo = je ^ 1;         // first j with (i+j) odd
-            {
-                const int w0 = i + je;
-                Ev[w0] = mad_lo_cc(a[je], b[i], Ev[w0]);
-                Ev[w0 + 1] = madc_hi_cc(a[je], b[i], Ev[w0 + 1]);
-#pragma unroll
-                for (int j = je + 2; j < N; j += 2) {
-                    Ev[i + j] = madc_lo_cc(a[j], b[i], Ev[i + j]);
-                    Ev[i + j + 1] = madc_hi_cc(a[j], b[i], Ev[i + j + 1]);
-                }
-                Ev[w0 + N] = addc(Ev[w0 + N], 0);      // so far only carries live up there: cannot overflow
-            }
-            {
-                const int w0 = i + jo - 1;
-                Od[w0] = mad_lo_cc(a[jo], b[i], Od[w0]);
-                Od[w0 + 1] = madc_hi_cc(a[jo], b[i], Od[w0 + 1]);
-#pragma unroll
-                for (int j = jo + 2; j < N; j += 2) {
-                    Od[i + j - 1] = madc_lo_cc(a[j], b[i], Od[i + j - 1]);
-                    Od[i + j] = madc_hi_cc(a[j], b[i], Od[i + j]);
-                }
-                if (w0 + N < 2 * N) Od[w0 + N] = addc(Od[w0 + N], 0);
-            }
-        }
-        v[0] = Ev[0];
-        v[1] = add_cc(Ev[1], Od[0]);
-#pragma unroll
-        for (int k = 2; k < 2 * N - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
-        v[2 * N - 1] = addc(Ev[2 * N - 1], Od[2 * N - 2]);
-    }
-    // v[0..W) = Ev + (Od << 32)
-    static B200_HD void wide_merge(uint32_t* v, const uint32_t* Ev, const uint32_t* Od) {
-        v[0] = Ev[0];
-        v[1] = add_cc(Ev[1], Od[0]);
-#pragma unroll
-        for (int k = 2; k < W - 1; k++) v[k] = addc_cc(Ev[k], Od[k - 1]);
-        v[W - 1] = addc(Ev[W - 1], Od[W - 2]);
-    }
-    // T[0..2N) += a * b, in place.  T itself is the even-aligned accumulator of the operand scanning above (its words may be
-    // full: every chain below is a carry chain over the words it touches); the odd-aligned partial sums go to a fresh Od
-    // (Od[k] = word k + 1) that is merged once at the end.  The carry that leaves the top of a row's chain -- T's or Od's --
-    // is deposited in Od one word above the chain: up there Od holds nothing but earlier carries, so the deposit cannot
-    // overflow and the next rows' chains absorb it.  144 IMAD.WIDE + 22 deposits + 23 merge additions per product, no
-    // separate product array and no wide addition (wide_mul + wide_add: 25 more instructions and 24 more registers).
-    // The sum stays below 2^(64N) by the compiler's bounds (dot_bounds), so nothing leaves word 2N - 1.
+    static constexpr int AW = 2 * N + 2;         // words of an even / odd accumulator array (redc)
+    // T[0..2N) += a * b, in place.  Operand scanning with the partial products split by the parity of their word position:
+    // a[j]*b[i] lands on word i+j; every 32x32 product is one IMAD.WIDE.U32.X inside a carry chain (two independent chains
+    // per row) -- one instruction per multiply-accumulate, against two for a product-scanning column sum.  T itself is the
+    // even-aligned accumulator (its words may be full: every chain below is a carry chain over the words it touches); the
+    // odd-aligned partial sums go to a fresh Od (Od[k] = word k + 1) that is merged once at the end.  The carry that leaves
+    // the top of a row's chain -- T's or Od's -- is deposited in Od one word above the chain: up there Od holds nothing but
+    // earlier carries, so the deposit cannot overflow and the next rows' chains absorb it.  144 IMAD.WIDE + 22 deposits +
+    // 23 merge additions per product; round 1 formed the product in a separate array and added it (25 more instructions,
+    // 24 more registers).  The sum stays below 2^(64N) by the compiler's bounds (dot_bounds): nothing leaves word 2N - 1.
     static B200_HD void wide_mac(uint32_t* T, const uint32_t* a, const uint32_t* b) {
         uint32_t Od[2 * N - 1];
         // row 0: T's chain accumulates, Od starts from plain products
@@ -242,26 +178,6 @@ struct Vm {
             a1 = s;
         }
         if (m & VM_DBL) { shl1(a0); shl1(a1); }
-    }
-    // acc (W words) += v (2N words: one product)
-    static B200_HD void wide_add(uint32_t* acc, const uint32_t* v) {
-        acc[0] = add_cc(acc[0], v[0]);
-#pragma unroll
-        for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], v[k]);
-        acc[2 * N] = addc(acc[2 * N], 0);
-    }
-    // acc +/-= v, W words each
-    static B200_HD void wide_addw(uint32_t* acc, const uint32_t* v) {
-        acc[0] = add_cc(acc[0], v[0]);
-#pragma unroll
-        for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], v[k]);
-        acc[2 * N] = addc(acc[2 * N], v[2 * N]);
-    }
-    static B200_HD void wide_subw(uint32_t* acc, const uint32_t* v) {
-        acc[0] = sub_cc(acc[0], v[0]);
-#pragma unroll
-        for (int k = 1; k < 2 * N; k++) acc[k] = subc_cc(acc[k], v[k]);
-        acc[2 * N] = subc(acc[2 * N], v[2 * N]);
     }
     // Montgomery reduction of a wide value T < 4 p R (T[0..2N), top word zero) -> canonical residue T / R mod p.
     // Word-sliding reduction on an even / odd split of T: no data movement, the window offsets are compile-time.
@@ -572,114 +488,147 @@ struct Vm {
     // ---------------------------------------------------------------------------------------------------
     static B200_HD_NOINLINE void split_stage1(uint32_t* slots, const uint32_t* kbank, uint32_t b1, uint32_t b2, uint32_t b3,
                                               uint32_t live, const uint32_t* w, int sub, uint32_t* xch) {
-        Ctx c;
-        c.slots = slots; c.kbank = kbank; c.base[0] = b1; c.base[1] = b2; c.base[2] = b3; c.live = live;
+        const uint32_t bases = (b1 << 8) | (b2 << 16) | (b3 << 24);
+        const kboff_t kb_off = (kboff_t)(kbank - slots);
         const uint32_t hdr = w[0];
         if ((hdr & 15) != VM_DOT) return;
         const uint32_t nt = (hdr >> 4) & 15, pred = (hdr >> 16) & 3;
-        if (pred && !((c.live >> (pred - 1)) & 1)) return;
-        uint32_t Tacc[W];
+        if (pred && !((live >> (pred - 1)) & 1)) return;
+        uint32_t Tacc[2 * N];
 #pragma unroll
-        for (int k = 0; k < W; k++) Tacc[k] = 0;
+        for (int k = 0; k < 2 * N; k++) Tacc[k] = 0;
         for (uint32_t t = 0; t < nt; t++) {
             const uint32_t tw = w[2 + t];
-            E2 a, b;
-            load2(a, operand_ptr(c, tw & 0x7FF));
-            const uint32_t am = (tw >> 22) & 15;
-            if (am) apply_mod(a, am);
-            const uint32_t bm = (tw >> 26) & 15;
-            load2(b, operand_ptr(c, (tw >> 11) & 0x7FF));
-            if (bm & (VM_REAL0 | VM_REAL1)) {
-                if (bm & VM_REAL1) b.c0 = b.c1;
-                F::zero(b.c1);                               // real scalar s = (s, 0)
-            } else if (bm & 3) {
-                apply_mod(b, bm & 3);
+            const uint32_t* pa = slot_ptr(slots, kb_off, bases, tw & 0x7FF);
+            const uint32_t* pb = slot_ptr(slots, kb_off, bases, (tw >> 11) & 0x7FF);
+            const uint32_t am = (tw >> 22) & 15, bm = (tw >> 26) & 15;
+            E1 a0, a1, b0, b1x, sa, sb;
+            if (C::LAZY_MODS) {
+                load1(a0, pa);
+                load1(a1, pa + N);
+                if (am) lazy_mods(a0, a1, am);
+            } else {
+                E2 a;
+                load2(a, pa);
+                if (am) apply_mod(a, am);
+                a0 = a.c0; a1 = a.c1;
             }
-            // this lane's factor pair: (a0, b0), (a1, b1) or the plain sums (a0 + a1, b0 + b1) (< 2p each)
-            uint32_t xa[N], xb[N], sa[N], sb[N];
-            sa[0] = add_cc(a.c0.l[0], a.c1.l[0]);
-#pragma unroll
-            for (int i = 1; i < N; i++) sa[i] = addc_cc(a.c0.l[i], a.c1.l[i]);
-            sb[0] = add_cc(b.c0.l[0], b.c1.l[0]);
-#pragma unroll
-            for (int i = 1; i < N; i++) sb[i] = addc_cc(b.c0.l[i], b.c1.l[i]);
+            if (bm & (VM_REAL0 | VM_REAL1)) {               // real scalar s = (s, 0)
+                load1(b0, pb + ((bm & VM_REAL1) ? N : 0));
+                F::zero(b1x);
+            } else {
+                load1(b0, pb);
+                load1(b1x, pb + N);
+                if (bm & VM_NEG) p_minus_c(b0);
+                if (((bm & VM_NEG) != 0) != ((bm & VM_CONJ) != 0)) p_minus_c(b1x);
+            }
+            // this lane's factor pair: (a0, b0), (a1, b1) or the plain sums (a0 + a1, b0 + b1)
+            add_nr(sa, a0, a1);
+            add_nr(sb, b0, b1x);
+            uint32_t xa[N], xb[N];
 #pragma unroll
             for (int i = 0; i < N; i++) {
-                xa[i] = sub == 0 ? a.c0.l[i] : (sub == 1 ? a.c1.l[i] : sa[i]);
-                xb[i] = sub == 0 ? b.c0.l[i] : (sub == 1 ? b.c1.l[i] : sb[i]);
+                xa[i] = sub == 0 ? a0.l[i] : (sub == 1 ? a1.l[i] : sa.l[i]);
+                xb[i] = sub == 0 ? b0.l[i] : (sub == 1 ? b1x.l[i] : sb.l[i]);
             }
-            uint32_t v[2 * N];
-            wide_mul(v, xa, xb);
-            wide_add(Tacc, v);
+            wide_mac(Tacc, xa, xb);
         }
         uint32_t* mine = xch + sub * W;
 #pragma unroll
-        for (int k = 0; k < W; k++) mine[k] = Tacc[k];
+        for (int k = 0; k < 2 * N; k++) mine[k] = Tacc[k];
     }
     static B200_HD_NOINLINE void split_stage2(uint32_t* slots, const uint32_t* kbank, uint32_t b1, uint32_t b2, uint32_t b3,
                                               uint32_t live, const uint32_t* w, int sub, const uint32_t* xch) {
-        Ctx c;
-        c.slots = slots; c.kbank = kbank; c.base[0] = b1; c.base[1] = b2; c.base[2] = b3; c.live = live;
+        const uint32_t bases = (b1 << 8) | (b2 << 16) | (b3 << 24);
+        const kboff_t kb_off = (kboff_t)(kbank - slots);
         const uint32_t hdr = w[0];
         const uint32_t kind = hdr & 15;
         if (kind == VM_NOP || sub == 2) return;
         const uint32_t nl = (hdr >> 8) & 15;
         const uint32_t scale = (hdr >> 12) & 7, halve = (hdr >> 15) & 1, pred = (hdr >> 16) & 3;
-        uint32_t* dst = const_cast<uint32_t*>(operand_ptr(c, w[1] & 0x7FF)) + sub * N;        // this lane's component
-        if (pred && !((c.live >> (pred - 1)) & 1)) {
-            const uint32_t* src = operand_ptr(c, (w[1] >> 16) & 0x7FF) + sub * N;
+        uint32_t* dst = const_cast<uint32_t*>(slot_ptr(slots, kb_off, bases, w[1] & 0x7FF)) + sub * N;   // this lane's component
+        if (pred && !((live >> (pred - 1)) & 1)) {
+            const uint32_t* src = slot_ptr(slots, kb_off, bases, (w[1] >> 16) & 0x7FF) + sub * N;
             for (int i = 0; i < N; i++) dst[i] = src[i];
             return;
         }
         if (kind == VM_INV) {
             if (sub == 0) {
                 E2 a, res;
-                load2(a, operand_ptr(c, w[2] & 0x7FF));
+                load2(a, slot_ptr(slots, kb_off, bases, w[2] & 0x7FF));
                 T::f2_inv(res, a);
                 store2(dst, res);
             }
             return;
         }
         E1 r;
+        bool folded = false;
         if (kind == VM_DOT) {
-            uint32_t V[W], U[W];
+            uint32_t V[2 * N], U[2 * N];
             const uint32_t levels = (hdr >> 18) & 3;
             if (sub == 0) {                                  // RE = off p^2 + T0 - |BETA| T1
                 const uint32_t* off = C::K().p2 + ((hdr >> 24) & 31) * (2 * N);
 #pragma unroll
-                for (int k = 0; k < 2 * N; k++) V[k] = off[k];
-                V[2 * N] = 0;
+                for (int k = 0; k < 2 * N; k++) { V[k] = off[k]; U[k] = xch[k]; }
+                wide_add2n(V, U);
 #pragma unroll
-                for (int k = 0; k < W; k++) U[k] = xch[k];
-                wide_addw(V, U);
-#pragma unroll
-                for (int k = 0; k < W; k++) U[k] = xch[W + k];
-                wide_subw(V, U);
-                if (C::BETA == -5) { wide_subw(V, U); wide_subw(V, U); wide_subw(V, U); wide_subw(V, U); }
+                for (int k = 0; k < 2 * N; k++) U[k] = xch[W + k];
+                wide_sub2n(V, U);
+                if (C::BETA == -5) { wide_sub2n(V, U); wide_sub2n(V, U); wide_sub2n(V, U); wide_sub2n(V, U); }
             } else {                                         // IM = T2 - T0 - T1
 #pragma unroll
-                for (int k = 0; k < W; k++) { V[k] = xch[2 * W + k]; U[k] = xch[k]; }
-                wide_subw(V, U);
+                for (int k = 0; k < 2 * N; k++) { V[k] = xch[2 * W + k]; U[k] = xch[k]; }
+                wide_sub2n(V, U);
 #pragma unroll
-                for (int k = 0; k < W; k++) U[k] = xch[W + k];
-                wide_subw(V, U);
+                for (int k = 0; k < 2 * N; k++) U[k] = xch[W + k];
+                wide_sub2n(V, U);
+            }
+            folded = ((hdr >> 29) & 1) != 0;
+            if (folded) {                                    // scale and linear tail before the reduction, as in exec_op
+                if (scale != 1) wide_scale(V, scale);
+                for (uint32_t t = 0; t < nl; t++) {
+                    const uint32_t lw = w[8 + t];
+                    const uint32_t* px = slot_ptr(slots, kb_off, bases, lw & 0x7FF);
+                    int coef = (int)((lw >> 11) & 31);
+                    if (coef >= 16) coef -= 32;
+                    uint32_t m = (lw >> 16) & 15;
+                    if (coef < 0) m ^= VM_NEG;
+                    const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+                    E1 x0, x1;
+                    if (C::LAZY_MODS) {
+                        load1(x0, px);
+                        load1(x1, px + N);
+                        if (m) lazy_mods(x0, x1, m);
+                    } else {
+                        E2 x;
+                        load2(x, px);
+                        if (m & ~VM_NEG) apply_mod(x, m & ~VM_NEG);
+                        x0 = x.c0; x1 = x.c1;
+                        if (m & VM_NEG) { p_minus_c(x0); p_minus_c(x1); }
+                    }
+                    E1 xc = sub == 0 ? x0 : x1;
+                    if (mag != 1) small_multiple_nr(xc, mag);
+                    wide_add_high(V, xc);
+                }
             }
             redc(r, V, levels);
-            if (scale != 1) mul_small(r, r, scale);
+            if (!folded && scale != 1) mul_small(r, r, scale);
         } else {
             F::zero(r);
         }
-        for (uint32_t t = 0; t < nl; t++) {
-            const uint32_t lw = w[8 + t];
-            E2 x;
-            load2(x, operand_ptr(c, lw & 0x7FF));
-            apply_mod(x, (lw >> 16) & 15);
-            E1 xc = sub == 0 ? x.c0 : x.c1;
-            int coef = (int)((lw >> 11) & 31);
-            if (coef >= 16) coef -= 32;
-            const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
-            if (mag != 1) mul_small(xc, xc, mag);
-            if (coef < 0) F::sub(r, r, xc); else F::add(r, r, xc);
+        if (!folded) {
+            for (uint32_t t = 0; t < nl; t++) {
+                const uint32_t lw = w[8 + t];
+                E2 x;
+                load2(x, slot_ptr(slots, kb_off, bases, lw & 0x7FF));
+                apply_mod(x, (lw >> 16) & 15);
+                E1 xc = sub == 0 ? x.c0 : x.c1;
+                int coef = (int)((lw >> 11) & 31);
+                if (coef >= 16) coef -= 32;
+                const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+                if (mag != 1) mul_small(xc, xc, mag);
+                if (coef < 0) F::sub(r, r, xc); else F::add(r, r, xc);
+            }
         }
         if (halve) F::halve(r, r);
         for (int i = 0; i < N; i++) dst[i] = r.l[i];

@@ -444,6 +444,13 @@ class Curve:
         check(lib.b200_g1_msm(self.id, n, buf_ptr(pts) if n else None, buf_ptr(scalars) if n else None, out, flags))
         return out.raw
 
+    def G2MsmBatch(self, pts, scalars, n, flags=0):
+        """sum_i [k_i] Q_i over G2 (G2 MSM); pts = n G2.Bytes() encodings, scalars = n x 32 bytes big-endian"""
+        lib = load()
+        out = ctypes.create_string_buffer(self.G2ByteSize)
+        check(lib.b200_g2_msm(self.id, n, buf_ptr(pts) if n else None, buf_ptr(scalars) if n else None, out, flags))
+        return out.raw
+
 
 # mathlib.Curves analogue: index by CurveID (reference math.go:142-255); unsupported ids are None
 Curves = [None] * 8

@@ -109,6 +109,37 @@ def test_msm_golden(m, cid):
         assert out.hex() == case["out"], "n=%d" % n
 
 
+@pytest.mark.parametrize("cid", [1, 4, 5])
+def test_g2_msm_matches_oracle(m, cid):
+    """b200_g2_msm against the oracle's sum of [k_i]Q_i: empty, one point, infinity / zero scalar / repeated /
+    opposite points, scalars at and above r, and a few hundred random terms (several buckets per window get > 1 point)."""
+    import random
+    from oracle import codec
+    from oracle.pairing import Pairing
+    from oracle.params import CURVE_IDS as ORACLE_IDS
+    c = m.Curves[cid]
+    P, _ = ORACLE_IDS[cid]
+    C = Pairing(P).C
+    rnd = random.Random(900 + cid)
+    base = [C.g2_mul(C.g2, rnd.randrange(1, P.r)) for _ in range(12)]
+
+    def run(points, scalars):
+        want = None
+        for q, k in zip(points, scalars):
+            want = C.g2_add(want, C.g2_mul(q, k % P.r)) if q is not None else want
+        pts = b"".join(codec.g2_to_bytes(P, q) for q in points)
+        ks = b"".join(k.to_bytes(32, "big") for k in scalars)
+        assert c.G2MsmBatch(pts, ks, len(points)) == codec.g2_to_bytes(P, want)
+
+    run([], [])
+    run([base[0]], [5])
+    run([base[0], None, base[1], base[1], C.g2_neg(base[1]), base[2]], [0, 77, 3, 4, 7, P.r + 9])     # = 9 base[2]
+    run([base[0], C.g2_neg(base[0])], [11, 11])                                                      # cancels to infinity
+    run([base[i % 12] for i in range(40)], [(1 << 256) - 1 - i for i in range(40)])
+    n = 300
+    run([base[rnd.randrange(12)] for _ in range(n)], [rnd.randrange(P.r) for _ in range(n)])
+
+
 @pytest.mark.parametrize("cid", CURVE_IDS)
 def test_mont_encoding_roundtrip(m, cid):
     """OUT_MONT then IN_MONT must reproduce the BYTES results (zero-conversion path for Go slabs)."""

@@ -850,6 +850,10 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
     ms = timed(lambda: m.check(lib.b200_g2_mul_batch(5, n6, g2.data_ptr(), d_kr.data_ptr(), o2.data_ptr(), m.DEVICE_PTRS)),
                reps=2)
     out["next_g2_mul_bls12_381_16384"] = {"ms": ms, "muls_per_s": n6 / ms * 1e3}
+    # G2 MSM over the n6 points just produced (distinct multiples of the generator), scalars uniform in [0, r)
+    o3 = torch.empty(c.G2ByteSize, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: m.check(lib.b200_g2_msm(5, n6, o2.data_ptr(), d_kr.data_ptr(), o3.data_ptr(), m.DEVICE_PTRS)), reps=2)
+    out["next_g2_msm_bls12_381_16384"] = {"latency_ms": ms, "points_per_s": n6 / ms * 1e3}
     return out
 
 

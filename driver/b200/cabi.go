@@ -101,6 +101,19 @@ func g2MulBatch(curve int, n int, pts, scalars []byte, flags uint32) []byte {
 	return out
 }
 
+func g2Msm(curve int, n int, pts, scalars []byte, g2Size int, flags uint32) []byte {
+	out := make([]byte, g2Size)
+	check("g2 multi scalar mul", C.b200_g2_msm(C.int(curve), C.size_t(n), ptr(pts), ptr(scalars), ptr(out), C.uint32_t(flags)))
+	return out
+}
+
+// g1NormalizeBatch: n Jacobian points as Montgomery limbs X|Y|Z -> n affine Bytes() encodings (one inversion per 8 points).
+func g1NormalizeBatch(curve int, n int, jac []byte, g1Size int) []byte {
+	out := make([]byte, n*g1Size)
+	check("g1 normalize", C.b200_g1_normalize_batch(C.int(curve), C.size_t(n), ptr(jac), ptr(out), 0))
+	return out
+}
+
 func g2Sum(curve int, n int, pts []byte, g2Size int) []byte {
 	out := make([]byte, g2Size)
 	check("g2 sum", C.b200_g2_sum(C.int(curve), C.size_t(n), ptr(pts), ptr(out), 0))

@@ -108,6 +108,26 @@ func (c *Curve) VerifyBatch(n int, g1a, g2a, g1b, g2b []byte) []byte {
 
 func (c *Curve) G1MulBatch(n int, pts, scalars []byte) []byte { return g1MulBatch(c.id, n, pts, scalars, 0) }
 
+// MultiScalarMulG2: sum [b_i]a_i over G2 in one Pippenger run (SURVEY 8f-3); a length mismatch yields infinity like
+// MultiScalarMul.
+func (c *Curve) MultiScalarMulG2(a []driver.G2, b []driver.Zr) driver.G2 {
+	if len(a) != len(b) {
+		return c.NewG2()
+	}
+	pts := make([]byte, 0, len(a)*c.g2Size())
+	ks := make([]byte, 0, len(a)*32)
+	for i := range a {
+		pts = append(pts, a[i].(*G2).raw...)
+		ks = append(ks, b[i].Bytes()...)
+	}
+	return &G2{c: c, raw: g2Msm(c.id, len(a), pts, ks, c.g2Size(), 0)}
+}
+
+// G1NormalizeBatch: Jacobian Montgomery slabs (kilic PointG1 / gnark G1Jac memory) -> affine Bytes(), batched inversion.
+func (c *Curve) G1NormalizeBatch(n int, jacobianMont []byte) []byte {
+	return g1NormalizeBatch(c.id, n, jacobianMont, c.g1Size())
+}
+
 // ---- the remaining driver.Curve methods: host bookkeeping ---------------------------------------------------------
 
 func (c *Curve) GenG1() driver.G1 { return &G1{c: c, raw: append([]byte(nil), c.g1Gen...)} }

@@ -78,6 +78,18 @@ struct Curve {
         check("multi scalar mul", b200_g1_msm(id, a.size(), pts.data(), ks.data(), r.raw.data(), 0));
         return r;
     }
+    // G2 counterpart of multiScalarMul: sum [b_i]a_i over the twist, one Pippenger run on the device
+    G2 multiScalarMulG2(const std::vector<G2>& a, const std::vector<Zr>& b) const {
+        G2 r; r.raw.assign(g2Size(), 0);
+        if (a.size() != b.size()) { if (fp == 48) r.raw[0] = 0x40; return r; }
+        Bytes pts, ks;
+        for (size_t i = 0; i < a.size(); i++) {
+            pts.insert(pts.end(), a[i].raw.begin(), a[i].raw.end());
+            ks.insert(ks.end(), b[i].be32.begin(), b[i].be32.end());
+        }
+        check("g2 multi scalar mul", b200_g2_msm(id, a.size(), pts.data(), ks.data(), r.raw.data(), 0));
+        return r;
+    }
     // callers next to the hot path (reference driver/math.go:307-310, 344-359)
     G2 g2Mul(const G2& p, const Zr& a) const {
         G2 r; r.raw.resize(g2Size());

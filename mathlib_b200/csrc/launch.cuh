@@ -430,19 +430,20 @@ struct Launch {
             msm_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(n, pl, b.digits, b.cursor, b.sorted);
             B200_COUNT_LAUNCH();
         }
-        if ((e = cudaMemsetAsync(b.size_hist, 0, 2 * B200_MSM_SIZE_BINS * sizeof(uint32_t), s)) != cudaSuccess) return e;
-        msm_size_hist_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist);
-        msm_size_scan_kernel<<<1, B200_MSM_SIZE_BINS, 0, s>>>(b.size_hist, b.size_hist + B200_MSM_SIZE_BINS);
-        msm_size_scatter_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist + B200_MSM_SIZE_BINS, b.perm);
-        B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
         if (b.max_heavy) {
             if ((e = cudaMemsetAsync(b.heavy_n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
             msm_heavy_list_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.heavy_n, (MsmHeavyItem*)b.heavy_items,
                                                                       b.max_heavy);
             B200_COUNT_LAUNCH();
         }
-        msm_accumulate_kernel<C, G, (IS_G1 ? B200_MSM_ACC_MIN_BLOCKS : 2)><<<blocks_for(nb, 128), 128, 0, s>>>(n, pl, (const Aff*)pts, b.offsets,
-                                                                    b.counts, b.sorted, b.perm, (Pt*)b.buckets);
+        // buckets in order of decreasing size (equal work per warp), then one thread per bucket
+        if ((e = cudaMemsetAsync(b.size_hist, 0, 2 * B200_MSM_SIZE_BINS * sizeof(uint32_t), s)) != cudaSuccess) return e;
+        msm_size_hist_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist);
+        msm_size_scan_kernel<<<1, B200_MSM_SIZE_BINS, 0, s>>>(b.size_hist, b.size_hist + B200_MSM_SIZE_BINS);
+        msm_size_scatter_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist + B200_MSM_SIZE_BINS, b.perm, 0u);
+        B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
+        msm_accumulate_kernel<C, G, (IS_G1 ? B200_MSM_ACC_MIN_BLOCKS : 2)><<<blocks_for(nb, 128), 128, 0, s>>>(
+            n, pl, (const Aff*)pts, b.offsets, b.counts, b.sorted, b.perm, (Pt*)b.buckets, nb);
         B200_COUNT_LAUNCH();
         if (b.max_heavy) {
             // long runs (more than B200_MSM_SEG points in one bucket): split over extra threads; empty for uniform scalars
@@ -454,6 +455,9 @@ struct Launch {
                                                          (const Pt*)b.heavy_partial, (Pt*)b.buckets);
             B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
         }
+        // (Tried in round 2: accumulating the windows in four groups from the top while side streams reduce each finished
+        // group and run its share of the Horner chain.  The split accumulation lost more -- 6.0 -> 9.1 ms, the top window's
+        // large buckets no longer hide behind the other windows -- than the overlapped tail won)
         MsmPlan pt = pl;                             // plan of the tail (one window when the bucket arrays were folded)
         if constexpr (IS_G1) {
             if (pl.tables && pl.W > 1) {

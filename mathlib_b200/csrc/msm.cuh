@@ -202,12 +202,13 @@ static __global__ void msm_size_scan_kernel(const uint32_t* hist, uint32_t* star
     }
     start[B200_MSM_SIZE_BINS - 1 - i] = sh[i] - v;
 }
-static __global__ void msm_size_scatter_kernel(size_t nb, const uint32_t* counts, uint32_t* start, uint32_t* perm) {
+static __global__ void msm_size_scatter_kernel(size_t nb, const uint32_t* counts, uint32_t* start, uint32_t* perm, uint32_t base) {
+    // counts / perm already point at this launch's range of buckets; the ids written are global (base + local index)
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
     uint32_t c = counts[t];
     uint32_t pos = atomicAdd(&start[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
-    perm[pos] = (uint32_t)t;
+    perm[pos] = base + (uint32_t)t;
 }
 
 // Long runs (skewed scalars: many equal digits) would serialise on one thread.  A bucket accumulates at most B200_MSM_SEG
@@ -275,9 +276,10 @@ msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const Ms
 template <class C, class G = G1Ops<C>, int MINB = B200_MSM_ACC_MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MINB)
 msm_accumulate_kernel(size_t n, MsmPlan pl, const typename G::Aff* pts, const uint32_t* offsets, const uint32_t* counts,
-                      const uint32_t* sorted, const uint32_t* perm, typename G::Pt* buckets) {
+                      const uint32_t* sorted, const uint32_t* perm, typename G::Pt* buckets, size_t nb) {
+    // perm[0..nb): the (window, bucket) ids this launch works on, largest buckets first
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (size_t)pl.W * pl.B) return;
+    if (tid >= nb) return;
     const size_t t = perm[tid];
     size_t w = t / pl.B;
     if (pl.tables) pts += w * pl.stride;
@@ -419,17 +421,17 @@ struct JacOps {
     }
 };
 
+// One warp: acc = 2^tail * sum_{w in [w_lo, w_hi)} 2^(start(w) - start(w_lo)) windows[w]  (Horner from the top window down, then
+// `tail` more doublings).  The chain is serial in the doublings, but inside a doubling three field products are independent
+// at each of the first two levels: lanes 0..2 take one each (every lane keeps a full copy of the point and repeats the
+// cheap additions), results are exchanged through shared memory.  4 product latencies per doubling instead of 8.
 template <class C>
-__global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_t* out, uint32_t flags) {
-    // One warp.  The Horner chain is serial in the doublings, but inside a doubling three field products are independent
-    // at each of the first two levels: lanes 0..2 take one each (every lane keeps a full copy of the point and repeats
-    // the cheap additions), results are exchanged through shared memory.  4 product latencies per doubling instead of 8.
-    if (blockIdx.x != 0) return;
+__device__ __forceinline__ void msm_horner_warp(const MsmPlan& pl, int w_lo, int w_hi, int tail, const G1XYZZ<C::N>* windows,
+                                                G1XYZZ<C::N>& acc, Fp<C::N>* sh) {
     typedef G1Ops<C> G;
     typedef FpOps<C> F;
     typedef JacOps<C> J;
     typedef typename F::E E;
-    __shared__ E sh[3];
     const int lane = threadIdx.x & 31;
     const int sel = lane < 2 ? lane : 2;
     // r0, r1, r2 = a0*b0, a1*b1, a2*b2, one product per lane
@@ -443,36 +445,38 @@ __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_
         r0 = sh[0]; r1 = sh[1]; r2 = sh[2];
         __syncwarp();
     };
-    typename G::Pt acc;
-    G::set_inf(acc);
-    for (int w = pl.W - 1; w >= 0; w--) {
-        if (!G::is_inf(acc) && pl.W > 1) {
-            // XYZZ (X, Y, ZZ, ZZZ) -> Jacobian with Z' = ZZ*ZZZ:  x = X/ZZ = (X*ZZ*ZZZ^2)/Z'^2, y = Y/ZZZ = (Y*ZZ^3*ZZZ^2)/Z'^3
-            typename J::Pt j;
-            E zz2, zzz2, t, u;
-            par3(zzz2, zz2, j.z, acc.zzz, acc.zzz, acc.zz, acc.zz, acc.zz, acc.zzz);
-            par3(t, u, zz2, acc.x, acc.zz, acc.y, zz2, zz2, zz2);           // t = X*ZZ, u = Y*ZZ^2 (third product unused)
-            F::mul(u, u, acc.zz);
-            par3(j.x, j.y, zz2, t, zzz2, u, zzz2, t, t);
-            for (int k = 0; k < msm_win_width(pl, w); k++) {                // dbl-2009-l, a = 0
-                E A, B, T, Cc, D, Fv, Ev, s;
-                par3(A, B, T, j.x, j.x, j.y, j.y, j.y, j.z);
-                F::add(s, j.x, B);
-                F::dbl(Ev, A); F::add(Ev, Ev, A);
-                par3(Cc, D, Fv, B, B, s, s, Ev, Ev);
-                F::sub(D, D, A); F::sub(D, D, Cc); F::dbl(D, D);
-                F::dbl(j.z, T);
-                F::sub(j.x, Fv, D); F::sub(j.x, j.x, D);
-                F::sub(s, D, j.x);
-                F::mul(s, Ev, s);
-                F::dbl(Cc, Cc); F::dbl(Cc, Cc); F::dbl(Cc, Cc);
-                F::sub(j.y, s, Cc);
-            }
-            // back to XYZZ: ZZ = Z^2, ZZZ = Z^3
-            acc.x = j.x; acc.y = j.y;
-            F::sqr(acc.zz, j.z);
-            F::mul(acc.zzz, acc.zz, j.z);
+    // acc <- 2^cnt acc through Jacobian coordinates
+    auto doublings = [&](int cnt) {
+        if (G::is_inf(acc) || cnt <= 0) return;
+        // XYZZ (X, Y, ZZ, ZZZ) -> Jacobian with Z' = ZZ*ZZZ:  x = X/ZZ = (X*ZZ*ZZZ^2)/Z'^2, y = Y/ZZZ = (Y*ZZ^3*ZZZ^2)/Z'^3
+        typename J::Pt j;
+        E zz2, zzz2, t, u;
+        par3(zzz2, zz2, j.z, acc.zzz, acc.zzz, acc.zz, acc.zz, acc.zz, acc.zzz);
+        par3(t, u, zz2, acc.x, acc.zz, acc.y, zz2, zz2, zz2);           // t = X*ZZ, u = Y*ZZ^2 (third product unused)
+        F::mul(u, u, acc.zz);
+        par3(j.x, j.y, zz2, t, zzz2, u, zzz2, t, t);
+        for (int k = 0; k < cnt; k++) {                                  // dbl-2009-l, a = 0
+            E A, B, T, Cc, D, Fv, Ev, s;
+            par3(A, B, T, j.x, j.x, j.y, j.y, j.y, j.z);
+            F::add(s, j.x, B);
+            F::dbl(Ev, A); F::add(Ev, Ev, A);
+            par3(Cc, D, Fv, B, B, s, s, Ev, Ev);
+            F::sub(D, D, A); F::sub(D, D, Cc); F::dbl(D, D);
+            F::dbl(j.z, T);
+            F::sub(j.x, Fv, D); F::sub(j.x, j.x, D);
+            F::sub(s, D, j.x);
+            F::mul(s, Ev, s);
+            F::dbl(Cc, Cc); F::dbl(Cc, Cc); F::dbl(Cc, Cc);
+            F::sub(j.y, s, Cc);
         }
+        // back to XYZZ: ZZ = Z^2, ZZZ = Z^3
+        acc.x = j.x; acc.y = j.y;
+        F::sqr(acc.zz, j.z);
+        F::mul(acc.zzz, acc.zz, j.z);
+    };
+    G::set_inf(acc);
+    for (int w = w_hi - 1; w >= w_lo; w--) {
+        if (w + 1 < w_hi) doublings(msm_win_width(pl, w));
         typename G::Pt v = windows[w];
         // acc += v (add-2008-s) with the independent products spread over the three lanes: 5 product latencies, not 14.
         // Infinity operands and equal / opposite points (warp-uniform conditions) take the complete serial adder.
@@ -498,9 +502,20 @@ __global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_
         F::sub(acc.y, u, S1);
         acc.x = t;
     }
+    doublings(tail);
+}
+
+// Horner over all windows, affine normalisation + store (one warp)
+template <class C>
+__global__ void msm_final_kernel(MsmPlan pl, const G1XYZZ<C::N>* windows, uint8_t* out, uint32_t flags) {
+    if (blockIdx.x != 0) return;
+    typedef G1Ops<C> G;
+    __shared__ Fp<C::N> sh[3];
+    typename G::Pt acc;
+    msm_horner_warp<C>(pl, 0, pl.W, 0, windows, acc, sh);
     typename G::Aff r;
     G::to_affine(r, acc);
-    if (lane == 0) Codec<C>::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);
+    if ((threadIdx.x & 31) == 0) Codec<C>::g1_store(out, r.x, r.y, flags & FLAG_OUT_MONT);
 }
 
 // ---- G2 MSM: the same pipeline over E'(Fp2).  Points: reference G2.Bytes() encodings (or Montgomery

@@ -53,7 +53,7 @@ def launches(csv_path, out_path, command):
         a[2] += m.get("dram__bytes_read.sum", 0.0)
         a[3] += m.get("dram__bytes_write.sum", 0.0)
     total = sum(a[1] for a in agg.values())
-    out = ["# Round 1: ncu launch list of `%s` (aggregated by kernel)" % command, "",
+    out = ["# ncu launch list of `%s` (aggregated by kernel)" % command, "",
            "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
            "--csv` (raw CSV: `%s`)." % out_path.replace(".md", ".csv").split("/")[-1],
            "Per-launch times are cold-cache and serialised; compare shares, not absolutes. The timed region of the headline "
@@ -65,15 +65,72 @@ def launches(csv_path, out_path, command):
     open(out_path, "w").write("\n".join(out) + "\n")
 
 
-def rep(rep_path, out_path, title, text):
-    raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def _opcode_mix(sass_csv_text, warps):
+    """opcode mix + per-warp instruction counts from an `ncu --page source --csv --print-source sass` dump"""
+    rows = list(csv.reader(io.StringIO(sass_csv_text)))
+    h = None
+    for i, r in enumerate(rows):
+        if "Instructions Executed" in r:
+            h, rows = r, rows[i + 1:]
+            break
+    if h is None:
+        return []
+    iS, iE, iT = h.index("Source"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
+    ops, thr, tot = collections.Counter(), collections.Counter(), 0
+    for r in rows:
+        if len(r) <= iT:
+            continue
+        t = re.sub(r"^@!?U?P\d+\s+", "", r[iS].strip())
+        op = ".".join(t.split()[0].split(".")[:2]) if t else "?"
+        e = int(r[iE])
+        ops[op] += e
+        thr[op] += int(r[iT])
+        tot += e
+    out = ["", "## Executed warp instructions by opcode (SASS page)", "",
+           "%.3f M warp instructions in total%s." % (tot / 1e6, (" = %.2f M per warp (%d warps)" % (tot / warps / 1e6, warps)) if warps else ""),
+           "", "| opcode | share | per warp | active lanes |", "|---|---|---|---|"]
+    for op, c in ops.most_common(14):
+        out.append("| `%s` | %.1f%% | %s | %.1f |" % (op, 100.0 * c / tot, ("%.0f k" % (c / warps / 1e3)) if warps else "-", thr[op] / max(c, 1)))
+    return out
+
+
+def rep(rep_path, out_path, title, text, row=0, warps=0):
+    """rep_path: an .ncu-rep, or the CSV of its raw page (`ncu -i x.ncu-rep --page raw --csv`); row = which captured kernel"""
+    if rep_path.endswith(".csv"):
+        raw = open(rep_path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    out = ["# " + title, "", text, "", "| metric | value | unit |", "|---|---|---|"]
+    hdr, units, vals = rows[0], rows[1], rows[2 + row]
+    out = ["# " + title, "", text, "", "Kernel: `%s`" % vals[hdr.index("Kernel Name")][:160] if "Kernel Name" in hdr else "", "",
+           "| metric | value | unit |", "|---|---|---|"]
     for m in METRICS:
         if m in hdr:
             i = hdr.index(m)
             out.append("| %s | %s | %s |" % (m, vals[i], units[i]))
+    stalls = [(h, vals[hdr.index(h)]) for h in hdr if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h]
+    out += ["", "## Warp stall reasons (cycles per issued instruction)", "", "| reason | value |", "|---|---|"]
+    for h, v in sorted(stalls, key=lambda kv: -float(kv[1] or 0)):
+        if float(v or 0) >= 0.01:
+            out.append("| %s | %s |" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
+    sass = None
+    if rep_path.endswith(".ncu-rep"):
+        cmd = ["ncu", "-i", rep_path, "--page", "source", "--csv", "--print-source", "sass"]
+        sass = subprocess.run(cmd, capture_output=True, text=True).stdout
+        # several kernels in one report: sections are separated by a "Kernel Name" line
+        parts = re.split(r'(?m)^"Kernel Name",', sass)[1:]
+        per = max(1, len(parts) // max(1, len(rows) - 2))      # ncu prints every kernel's section `per` times
+        if len(parts) > row * per:
+            sass = parts[row * per]
+    else:
+        gz = rep_path.replace("_raw.csv", "_sass.csv.gz")
+        try:
+            import gzip
+            sass = gzip.open(gz, "rt").read()
+        except OSError:
+            sass = None
+    if sass:
+        out += _opcode_mix(sass, warps)
     open(out_path, "w").write("\n".join(out) + "\n")
 
 
@@ -81,4 +138,5 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
-        rep(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "")
+        rep(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "",
+            int(sys.argv[6]) if len(sys.argv) > 6 else 0, int(sys.argv[7]) if len(sys.argv) > 7 else 0)

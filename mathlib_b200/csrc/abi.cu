@@ -67,6 +67,8 @@ bool curve_info(int curve, CurveInfo* ci) {
 struct Workspace {
     int dev = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // second stream: the MSM's point upload + conversion overlap the digit / sort kernels
+    cudaEvent_t ev_start = nullptr, ev_points = nullptr;
     uint8_t* buf = nullptr;
     size_t cap = 0;
     int* d_err = nullptr;
@@ -92,6 +94,9 @@ Workspace* ws_acquire(int dev) {
     Workspace* w = new Workspace();
     w->dev = dev;
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return nullptr; }
+    if (cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&w->ev_start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&w->ev_points, cudaEventDisableTiming) != cudaSuccess) { delete w; return nullptr; }
     if (cudaMalloc(&w->d_err, sizeof(int)) != cudaSuccess) { delete w; return nullptr; }
     return w;
 }
@@ -108,6 +113,7 @@ struct WsGuard {
         if (!w) return;
         cudaSetDevice(w->dev);
         cudaStreamSynchronize(w->stream);
+        cudaStreamSynchronize(w->copy_stream);
         ws_release(w);
     }
 };
@@ -229,6 +235,8 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
                  uint8_t** scalars_dev, uint8_t** pts_in_dev, size_t pts_in_bytes, uint8_t** out_dev, size_t gmul = 1) {
     // gmul = 1: G1 (coordinates in Fp), 2: G2 (coordinates in Fp2: twice the bytes per point)
     const size_t aff_size = vt->aff_size * gmul, xyzz_size = vt->xyzz_size * gmul;
+    const size_t n_sc = n;                 // scalars
+    if (pl.glv) n *= 2;                    // points / digits / sorted entries: P_i and phi(P_i)
     size_t off = 0;
     auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
     size_t nb = (size_t)pl.W * pl.B;
@@ -247,7 +255,7 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
     b->heavy_n = (uint32_t*)take(4);
     b->heavy_items = take((size_t)b->max_heavy * 8);
     b->heavy_partial = take((size_t)b->max_heavy * xyzz_size);
-    if (scalars_dev) *scalars_dev = take(n * 32);
+    if (scalars_dev) *scalars_dev = take(n_sc * 32);
     if (pts_in_dev) *pts_in_dev = take(pts_in_bytes);
     if (out_dev) *out_dev = take(2 * (size_t)vt->fp_bytes * gmul);
     return off;
@@ -264,21 +272,32 @@ int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const voi
     if (!g.w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
     Workspace& w = *g.w;
     CU(cudaSetDevice(dev));
-    MsmPlan pl = resident_plan(vt, bs, m);
+    bool need_points = resident_pts == nullptr;
+    // one-shot G1 MSM on a BLS12 curve: GLV split (the points are converted anyway, phi(P) is one more product each)
+    MsmPlan pl = (need_points && !g2 && vt->glv && m >= B200_MSM_GLV_MIN) ? msm_plan_glv(m) : resident_plan(vt, bs, m);
     MsmBuffers b;
     uint8_t *d_sc = nullptr, *d_pin = nullptr, *d_out = nullptr;
-    bool need_points = resident_pts == nullptr;
     size_t need = msm_carve(vt, pl, m, need_points, nullptr, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out, gmul);
     if (int rc = w.reserve(need)) return rc;
     msm_carve(vt, pl, m, need_points, w.buf, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out, gmul);
     CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
     const void* prepared = resident_pts;
+    b.points_ready = nullptr;
     if (m) {
+        if (need_points) {
+            // the points (2/3 of the bytes) upload and convert on the copy stream while the main stream uploads the scalars
+            // and runs the digit / scan / sort kernels, which need only the scalars; the bucket kernel waits on the event
+            CU(cudaEventRecord(w.ev_start, w.stream));                     // orders the slab's reuse after earlier work
+            CU(cudaStreamWaitEvent(w.copy_stream, w.ev_start, 0));
+            CU(cudaMemcpyAsync(d_pin, (const uint8_t*)pts + lo * g1sz, m * g1sz, cudaMemcpyHostToDevice, w.copy_stream));
+            if (g2) CU(vt->msm_points_g2(m, d_pin, b.points, kernel_flags(flags), w.d_err, w.copy_stream));
+            else CU(vt->msm_points(m, d_pin, b.points, kernel_flags(flags), w.d_err, w.copy_stream, pl.glv));
+            CU(cudaEventRecord(w.ev_points, w.copy_stream));
+            b.points_ready = w.ev_points;
+            prepared = b.points;
+        }
         CU(cudaMemcpyAsync(d_sc, (const uint8_t*)scalars + lo * 32, m * 32, cudaMemcpyHostToDevice, w.stream));
         if (need_points) {
-            CU(cudaMemcpyAsync(d_pin, (const uint8_t*)pts + lo * g1sz, m * g1sz, cudaMemcpyHostToDevice, w.stream));
-            CU((g2 ? vt->msm_points_g2 : vt->msm_points)(m, d_pin, b.points, kernel_flags(flags), w.d_err, w.stream));
-            prepared = b.points;
         } else {
             prepared = (const uint8_t*)resident_pts + lo * vt->aff_size;
         }
@@ -550,9 +569,9 @@ static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool 
     Workspace*& w = t_held.ws[std::make_pair(dev, t_stream)];
     if (!w) w = ws_acquire(dev);
     if (!w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
-    MsmPlan pl = resident_plan(vt, bs, n);
-    MsmBuffers b;
     bool need_points = !prepared;
+    MsmPlan pl = (need_points && !g2 && vt->glv && n >= B200_MSM_GLV_MIN) ? msm_plan_glv(n) : resident_plan(vt, bs, n);
+    MsmBuffers b;
     const size_t gmul = g2 ? 2 : 1;
     size_t need = msm_carve(vt, pl, n, need_points, nullptr, &b, nullptr, nullptr, 0, nullptr, gmul);
     if (need > w->cap) {
@@ -562,7 +581,8 @@ static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool 
     msm_carve(vt, pl, n, need_points, w->buf, &b, nullptr, nullptr, 0, nullptr, gmul);
     const void* prep = pts;
     if (need_points && n) {
-        CU((g2 ? vt->msm_points_g2 : vt->msm_points)(n, (const uint8_t*)pts, b.points, kernel_flags(flags), device_err_flag(dev), t_stream));
+        if (g2) CU(vt->msm_points_g2(n, (const uint8_t*)pts, b.points, kernel_flags(flags), device_err_flag(dev), t_stream));
+        else CU(vt->msm_points(n, (const uint8_t*)pts, b.points, kernel_flags(flags), device_err_flag(dev), t_stream, pl.glv));
         prep = b.points;
     }
     CU((g2 ? vt->msm_g2 : vt->msm)(n, prep, (const uint8_t*)scalars, (uint8_t*)out, kernel_flags(flags), pl, b, t_stream));
@@ -917,7 +937,7 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
     size_t g1sz = 2 * (size_t)vt->fp_bytes;
     if (n) {
         if (flags & B200_DEVICE_PTRS) {
-            CU(vt->msm_points(n, (const uint8_t*)pts, d_pts, kernel_flags(flags), device_err_flag(dev), t_stream));
+            CU(vt->msm_points(n, (const uint8_t*)pts, d_pts, kernel_flags(flags), device_err_flag(dev), t_stream, 0));
             if (rows > 1) CU(vt->msm_tables(n, tp, n, d_pts, t_stream));
             CU(cudaStreamSynchronize(t_stream));
         } else {
@@ -927,7 +947,7 @@ int b200_bases_upload(int curve, size_t n, const void* pts, uint32_t flags, uint
             if (int rc = w.reserve(n * g1sz)) return rc;
             CU(cudaMemcpyAsync(w.buf, pts, n * g1sz, cudaMemcpyHostToDevice, w.stream));
             CU(cudaMemsetAsync(w.d_err, 0, sizeof(int), w.stream));
-            CU(vt->msm_points(n, w.buf, d_pts, kernel_flags(flags), w.d_err, w.stream));
+            CU(vt->msm_points(n, w.buf, d_pts, kernel_flags(flags), w.d_err, w.stream, 0));
             if (rows > 1) CU(vt->msm_tables(n, tp, n, d_pts, w.stream));
             int h_err = 0;
             CU(cudaMemcpyAsync(&h_err, w.d_err, sizeof(int), cudaMemcpyDeviceToHost, w.stream));

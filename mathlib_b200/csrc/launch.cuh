@@ -35,6 +35,7 @@ struct MsmBuffers {            // device pointers carved out of one workspace sl
     void* heavy_items;         // max_heavy * sizeof(MsmHeavyItem)
     void* heavy_partial;       // max_heavy * sizeof(G1XYZZ)
     uint32_t max_heavy;        // W * n / B200_MSM_SEG
+    cudaEvent_t points_ready = nullptr;   // if set: the bucket kernels wait for it (points prepared on another stream)
 };
 
 struct CurveVTable {
@@ -43,6 +44,7 @@ struct CurveVTable {
     int scalar_bits;
     size_t aff_size;           // sizeof(G1Affine<N>)
     size_t xyzz_size;          // sizeof(G1XYZZ<N>)
+    int glv;                   // 1: the curve has the GLV endomorphism constants (BLS12 family): one-shot MSMs split the scalars
     cudaError_t (*pairing)(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
                            const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
     cudaError_t (*fexp)(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
@@ -73,7 +75,8 @@ struct CurveVTable {
     cudaError_t (*hash_to_g1)(int bbs, size_t n, const uint8_t* msgs, const uint64_t* offsets, const uint8_t* dst, size_t dlen,
                               uint8_t* out, uint32_t flags, cudaStream_t s);
     // points -> Montgomery affine array (for MSM / resident bases)
-    cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s);
+    // glv != 0: out holds 2n points, P_i and phi(P_i) (MsmPlan.glv)
+    cudaError_t (*msm_points)(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s, int glv);
     // resident window tables: tab[w*stride + i] = 2^(c*w) * tab[i]
     cudaError_t (*msm_tables)(size_t n, const MsmPlan& pl, size_t stride, void* tab, cudaStream_t s);
     // MSM over prepared points
@@ -395,9 +398,9 @@ struct Launch {
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
-    static cudaError_t msm_points(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s) {
+    static cudaError_t msm_points(size_t n, const uint8_t* pts, void* out, uint32_t flags, int* err, cudaStream_t s, int glv) {
         if (n == 0) return cudaSuccess;
-        msm_points_kernel<C><<<blocks_for(n, 128), 128, 0, s>>>(n, pts, (G1Affine<C::N>*)out, flags, err);
+        msm_points_kernel<C><<<blocks_for(n, 128), 128, 0, s>>>(n, pts, (G1Affine<C::N>*)out, flags, err, glv);
         B200_COUNT_LAUNCH();
         return cudaGetLastError();
     }
@@ -421,6 +424,7 @@ struct Launch {
             msm_digits_kernel<C><<<blocks_for(n, 256), 256, 0, s>>>(n, scalars, pl, b.digits, b.counts);
             B200_COUNT_LAUNCH();
         }
+        if (pl.glv) n *= 2;                          // from here on: 2n points (P_i, phi(P_i)) with 130-bit scalars
         int st = pl.B >= 1024 ? 1024 : (pl.B >= 32 ? pl.B : 32);
         msm_scan_kernel<<<pl.W, st, st * sizeof(uint32_t), s>>>(pl, b.counts, b.offsets);
         B200_COUNT_LAUNCH();
@@ -442,6 +446,7 @@ struct Launch {
         msm_size_scan_kernel<<<1, B200_MSM_SIZE_BINS, 0, s>>>(b.size_hist, b.size_hist + B200_MSM_SIZE_BINS);
         msm_size_scatter_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.size_hist + B200_MSM_SIZE_BINS, b.perm, 0u);
         B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
+        if (b.points_ready && (e = cudaStreamWaitEvent(s, b.points_ready, 0)) != cudaSuccess) return e;
         msm_accumulate_kernel<C, G, (IS_G1 ? B200_MSM_ACC_MIN_BLOCKS : 2)><<<blocks_for(nb, 128), 128, 0, s>>>(
             n, pl, (const Aff*)pts, b.offsets, b.counts, b.sorted, b.perm, (Pt*)b.buckets, nb);
         B200_COUNT_LAUNCH();
@@ -500,6 +505,7 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
+                                      C::FAMILY == FAMILY_BLS12 ? 1 : 0,
                                       &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec, &g1_normalize,
                                       (C::N == 12 && C::BETA == -1) ? &hash_to_g1 : nullptr, &msm_points, &msm_tables, &msm, &msm_points_g2, &msm_g2};
         return &t;

@@ -32,6 +32,7 @@ struct MsmPlan {
     int tables;     // 1: points come from a resident window table, tab[w*stride + i] = 2^start(w) * P_i  (no Horner tail)
     unsigned long long stride;
     int narrow;     // the top `narrow` windows are c-1 bits wide (see msm_plan)
+    int glv;        // 1: scalars are split k = k1 + lambda k2 (130-bit halves) over 2n points P_i, phi(P_i) (see msm_plan_glv)
 };
 
 // Window w covers scalar bits [start, start + width).  The W windows tile the scalar exactly: the lower W - narrow ones
@@ -51,7 +52,7 @@ int msm_win_start(const MsmPlan& p, int w) {
     return w <= full ? w * p.c : full * p.c + (w - full) * (p.c - 1);
 }
 
-static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
+static inline MsmPlan msm_plan(size_t n, int scalar_bits, int force_c = 0) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     // window size: measured on B200 (tools/msm_sizes_probe.py).  Below ~2^17 points the run time is the latency of the
@@ -66,6 +67,7 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
     c += bias;
     if (c < 2) c = 2;
     if (c > 16) c = 16;
+    if (force_c) c = force_c;
     MsmPlan p;
     p.c = c;
     p.W = scalar_bits / c + 1;
@@ -86,13 +88,30 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits) {
     p.nchunks = p.B / p.chunk;
     p.tables = 0;
     p.stride = 0;
+    p.glv = 0;
     return p;
 }
 
+// GLV plan (BLS12 curves, one-shot MSM of n >= 2^15 points): every scalar is split k = k1 + lambda k2 with k1, k2 < 2^130
+// (g1.cuh glv_split; [lambda](x, y) = (beta x, y) costs one Fp product per point when the points are converted), so the MSM
+// runs over 2n points and 130-bit scalars: half the windows for the same number of bucket additions, and the serial
+// Horner tail is c (W - 1) = 113 doublings instead of 240.  Window sizes that tile 130 bits with at most W narrow windows:
+// c = 17 (2 x 17 + 6 x 16 bits, 8 windows), 15 (9 windows), 14 (10 windows).
+static inline MsmPlan msm_plan_glv(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= 2 * n) lg++;
+    const int c = lg >= 20 ? 17 : (lg >= 17 ? 15 : 14);
+    MsmPlan p = msm_plan(2 * n, 130, c);
+    p.glv = 1;
+    return p;
+}
+#define B200_MSM_GLV_MIN ((size_t)1 << 15)
+
 #if defined(__CUDACC__)
 
+// glv != 0: also out[n + i] = phi(P_i) = (beta x, y)  (infinity (0, 0) maps to itself)
 template <class C>
-__global__ void msm_points_kernel(size_t n, const uint8_t* pts, G1Affine<C::N>* out, uint32_t flags, int* err) {
+__global__ void msm_points_kernel(size_t n, const uint8_t* pts, G1Affine<C::N>* out, uint32_t flags, int* err, int glv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int e = 0;
@@ -100,6 +119,13 @@ __global__ void msm_points_kernel(size_t n, const uint8_t* pts, G1Affine<C::N>* 
     Codec<C>::g1_load(a.x, a.y, pts + i * Codec<C>::g1_size(), flags & FLAG_IN_MONT, &e);
     if (e) atomicExch(err, 1);
     out[i] = a;
+    if (glv) {
+        Fp<C::N> beta;
+        const uint32_t* bw = C::K().glv_beta;
+        for (int k = 0; k < C::N; k++) beta.l[k] = bw[k];
+        FpOps<C>::mulx(a.x, a.x, beta);
+        out[n + i] = a;
+    }
 }
 
 // k (8 LE words) mod r by repeated conditional subtraction (k < 2^256 < 14 r for all three curves)
@@ -118,15 +144,10 @@ __device__ __forceinline__ void scalar_reduce(uint32_t* k) {
     }
 }
 
-// digits[w*n + i] = signed digit of scalar i in window w, packed as (|d| << 1) | sign ; 0 = skip
-template <class C>
-__global__ void msm_digits_kernel(size_t n, const uint8_t* scalars, MsmPlan pl, uint32_t* digits, uint32_t* counts) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t k[9];
-    Codec<C>::scalar_load(k, scalars + i * 32);
-    scalar_reduce<C>(k);
-    k[8] = 0;
+// digits[w*stride + idx] = signed digit of the (<= 256-bit, zero-extended to 9 words) scalar k in window w, packed as
+// (|d| << 1) | sign ; 0 = skip
+__device__ __forceinline__ void msm_emit_digits(const uint32_t* k, size_t idx, size_t stride, const MsmPlan& pl, uint32_t* digits,
+                                                uint32_t* counts) {
     uint32_t carry = 0;
     for (int w = 0; w < pl.W; w++) {
         const int bit = msm_win_start(pl, w), cw = msm_win_width(pl, w);
@@ -137,9 +158,30 @@ __global__ void msm_digits_kernel(size_t n, const uint8_t* scalars, MsmPlan pl, 
         // signed digits: fold d > 2^(cw-1) to d - 2^cw with a carry into the next window; never on the top window
         if (w + 1 < pl.W && d > (1u << (cw - 1))) { d = (1u << cw) - d; neg = 1; carry = 1; } else carry = 0;
         uint32_t packed = d ? ((d << 1) | neg) : 0;
-        digits[(size_t)w * n + i] = packed;
+        digits[(size_t)w * stride + idx] = packed;
         if (d) atomicAdd(&counts[(size_t)w * pl.B + (d - 1)], 1u);
     }
+}
+template <class C>
+__global__ void msm_digits_kernel(size_t n, const uint8_t* scalars, MsmPlan pl, uint32_t* digits, uint32_t* counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[9];
+    Codec<C>::scalar_load(k, scalars + i * 32);
+    scalar_reduce<C>(k);
+    k[8] = 0;
+    if (!pl.glv) {
+        msm_emit_digits(k, i, n, pl, digits, counts);
+        return;
+    }
+    // GLV: point i takes k1, point n + i (= phi(P_i)) takes k2
+    uint32_t h[9];
+    uint32_t k1[5], k2[5];
+    G1Ops<C>::glv_split(k1, k2, k);
+    for (int j = 0; j < 9; j++) h[j] = j < 5 ? k1[j] : 0u;
+    msm_emit_digits(h, i, 2 * n, pl, digits, counts);
+    for (int j = 0; j < 5; j++) h[j] = k2[j];
+    msm_emit_digits(h, n + i, 2 * n, pl, digits, counts);
 }
 
 // per window exclusive scan of counts[w*B .. w*B+B) -> offsets (relative to the window), one block per window
@@ -181,11 +223,15 @@ static __global__ void msm_scatter_kernel(size_t n, MsmPlan pl, const uint32_t* 
 // Load balancing: buckets are handed to threads in order of decreasing size (counting sort of the bucket ids by
 // their point count, sizes clamped to 1023), so the 32 threads of a warp run the same number of mixed additions.
 #define B200_MSM_SIZE_BINS 1024
+// Empty buckets are common (signed digits leave half of a narrow window's buckets unused; small MSMs), and they would all
+// hit bin 0: their atomics are aggregated per warp (one atomicAdd per warp instead of up to 32).
 static __global__ void msm_size_hist_kernel(size_t nb, const uint32_t* counts, uint32_t* hist) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb) return;
-    uint32_t c = counts[t];
-    atomicAdd(&hist[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
+    const bool live = t < nb;
+    const uint32_t c = live ? counts[t] : 1u;
+    const unsigned zero = __ballot_sync(0xffffffffu, live && c == 0);
+    if (zero && (threadIdx.x & 31) == (unsigned)(__ffs(zero) - 1)) atomicAdd(&hist[0], (uint32_t)__popc(zero));
+    if (live && c) atomicAdd(&hist[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
 }
 // exclusive scan of hist in DESCENDING size order -> start[]; single block of B200_MSM_SIZE_BINS threads
 static __global__ void msm_size_scan_kernel(const uint32_t* hist, uint32_t* start) {
@@ -205,9 +251,20 @@ static __global__ void msm_size_scan_kernel(const uint32_t* hist, uint32_t* star
 static __global__ void msm_size_scatter_kernel(size_t nb, const uint32_t* counts, uint32_t* start, uint32_t* perm, uint32_t base) {
     // counts / perm already point at this launch's range of buckets; the ids written are global (base + local index)
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb) return;
-    uint32_t c = counts[t];
-    uint32_t pos = atomicAdd(&start[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
+    const bool live = t < nb;
+    const uint32_t c = live ? counts[t] : 1u;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned zero = __ballot_sync(0xffffffffu, live && c == 0);
+    uint32_t zbase = 0;
+    if (zero) {
+        const int leader = __ffs(zero) - 1;
+        if ((int)lane == leader) zbase = atomicAdd(&start[0], (uint32_t)__popc(zero));
+        zbase = __shfl_sync(0xffffffffu, zbase, leader);
+    }
+    if (!live) return;
+    uint32_t pos;
+    if (c == 0) pos = zbase + (uint32_t)__popc(zero & ((1u << lane) - 1));
+    else pos = atomicAdd(&start[c < B200_MSM_SIZE_BINS ? c : B200_MSM_SIZE_BINS - 1], 1u);
     perm[pos] = base + (uint32_t)t;
 }
 

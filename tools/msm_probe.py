@@ -8,9 +8,9 @@ lib.b200_set_stream(torch.cuda.current_stream().cuda_stream)
 cid = int(os.environ.get("CID", "5")); c = m.Curves[cid]
 lg = int(os.environ.get("LG", "20")); n = 1 << lg
 rng = np.random.default_rng(5)
+import bench
 def rand_scalars():
-    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); ks[:, 0] &= 0x0F
-    return torch.from_numpy(ks.reshape(-1)).to(dev)
+    return torch.from_numpy(bench.scalars_mod_r(rng, n, cid).reshape(-1)).to(dev)        # uniform in [0, r), as in bench.py
 d_k = rand_scalars()
 gen = torch.frombuffer(bytearray(c.GenG1.Bytes()), dtype=torch.uint8).to(dev).repeat(n)
 pts = torch.empty(n * c.G1ByteSize, dtype=torch.uint8, device=dev)

@@ -206,8 +206,10 @@ def emit(line):
 
 
 def msm_work_m(n, bits=255):
-    """Fp products of one Pippenger MSM with this library's plan (msm.cuh msm_plan: c = 16 from 2^17 points on):
-    n*W mixed additions (10 m) + the running-sum reduction of W * 2^(c-1) buckets (2 full additions of 14 m each)."""
+    """Algorithmic Fp products of one Pippenger MSM (the plan of msm.cuh msm_plan without GLV: c = 16 from 2^17 points on):
+    n*W mixed additions (10 m) + the running-sum reduction of W * 2^(c-1) buckets (2 full additions of 14 m each).  The
+    GLV plan the library uses for one-shot BLS12 MSMs does the same number of bucket additions (2n points x W/2 windows)
+    over the same number of buckets, so this stays the work figure of the roofline."""
     lg = n.bit_length() - 1
     c = (max(lg + 1, 7) if lg <= 13 else {14: 15, 15: 14, 16: 15}.get(lg, 16))
     w = bits // c + 1
@@ -648,8 +650,10 @@ def run_configs(m, lib, dev, stream, torch, dist, rank, world, args):
                         "frac": work_m * MAC_PER_M[12] / (ms_local * 1e-3) / IMAD_WIDE_PEAK,
                         "m_per_launch": work_m, "window_bits": cwin, "windows": nwin,
                         "hbm_GBps_algorithmic": nl * (g1sz + 32) / (ms_local * 1e-3) / 1e9,
-                        "note": "per rank: n*W mixed adds x 10 m + 2*W*2^(c-1) adds x 14 m, 300 MAC32 per m, over "
-                                "this rank's local MSM time; HBM bytes n*(2*FpBytes+32) are a secondary figure"},
+                        "note": "per rank: n*W mixed adds x 10 m + 2*W*2^(c-1) adds x 14 m (c-bit windows over the full "
+                                "scalar; the GLV plan in use does the same additions over 2n points and W/2 windows), 300 "
+                                "MAC32 per m, over this rank's local MSM time; HBM bytes n*(2*FpBytes+32) are a secondary "
+                                "figure"},
            "what": "points (Montgomery slab) and scalars already in HBM; scalars uniform in [0, r)"}
     # oracle check + CPU baseline of the same 2^20-point problem (rank 0, all host threads)
     if rank == 0:

@@ -251,7 +251,7 @@ size_t msm_carve(const CurveVTable* vt, const MsmPlan& pl, size_t n, bool need_p
     b->buckets = take(nb * xyzz_size);
     b->chunks = take((size_t)pl.W * pl.nchunks * xyzz_size);
     b->windows = take((size_t)pl.W * 9 * xyzz_size);      // W window sums + 8 partial sums per window
-    b->max_heavy = (uint32_t)(((size_t)pl.W * n) / 512);       // B200_MSM_SEG = 512 points per segment
+    b->max_heavy = (uint32_t)(((size_t)pl.W * n) / (size_t)pl.seg);     // extra segments of runs longer than pl.seg points
     b->heavy_n = (uint32_t*)take(4);
     b->heavy_items = take((size_t)b->max_heavy * 8);
     b->heavy_partial = take((size_t)b->max_heavy * xyzz_size);
@@ -274,7 +274,7 @@ int msm_host_range(const CurveInfo& ci, int dev, size_t lo, size_t hi, const voi
     CU(cudaSetDevice(dev));
     bool need_points = resident_pts == nullptr;
     // one-shot G1 MSM on a BLS12 curve: GLV split (the points are converted anyway, phi(P) is one more product each)
-    MsmPlan pl = (need_points && !g2 && vt->glv && m >= B200_MSM_GLV_MIN) ? msm_plan_glv(m) : resident_plan(vt, bs, m);
+    MsmPlan pl = (need_points && !g2 && vt->glv && m >= B200_MSM_GLV_MIN) ? msm_plan_glv(m, vt->glv) : resident_plan(vt, bs, m);
     MsmBuffers b;
     uint8_t *d_sc = nullptr, *d_pin = nullptr, *d_out = nullptr;
     size_t need = msm_carve(vt, pl, m, need_points, nullptr, &b, &d_sc, need_points ? &d_pin : nullptr, m * g1sz, &d_out, gmul);
@@ -570,7 +570,7 @@ static int msm_device_ptrs(const CurveInfo& ci, size_t n, const void* pts, bool 
     if (!w) w = ws_acquire(dev);
     if (!w) return fail(B200_ERR_CUDA, "cannot create workspace on device %d", dev);
     bool need_points = !prepared;
-    MsmPlan pl = (need_points && !g2 && vt->glv && n >= B200_MSM_GLV_MIN) ? msm_plan_glv(n) : resident_plan(vt, bs, n);
+    MsmPlan pl = (need_points && !g2 && vt->glv && n >= B200_MSM_GLV_MIN) ? msm_plan_glv(n, vt->glv) : resident_plan(vt, bs, n);
     MsmBuffers b;
     const size_t gmul = g2 ? 2 : 1;
     size_t need = msm_carve(vt, pl, n, need_points, nullptr, &b, nullptr, nullptr, 0, nullptr, gmul);

@@ -75,6 +75,7 @@ struct BN254 {
     static constexpr bool X_NEG = false;
     static constexpr int FLAG_BITS = 2;
     static constexpr int SCALAR_BITS = 254;
+    static constexpr int GLV_BITS = 0;                // no GLV constants
     static B200_HD const CurveConsts<8>& K() { return B200_K(BN254); }
     static B200_HD const uint32_t* p() { return K().p; }
     static B200_HD const uint32_t* one() { return K().one; }
@@ -95,6 +96,7 @@ struct BLS381 {
     static constexpr bool X_NEG = true;
     static constexpr int FLAG_BITS = 3;
     static constexpr int SCALAR_BITS = 255;
+    static constexpr int GLV_BITS = 128;              // bit length of lambda = x^2 - 1: both halves of an exact GLV split fit
     static B200_HD const CurveConsts<12>& K() { return B200_K(BLS381); }
     static B200_HD const uint32_t* p() { return K().p; }
     static B200_HD const uint32_t* one() { return K().one; }
@@ -115,6 +117,7 @@ struct BLS377 {
     static constexpr bool X_NEG = false;
     static constexpr int FLAG_BITS = 3;
     static constexpr int SCALAR_BITS = 253;
+    static constexpr int GLV_BITS = 127;
     static B200_HD const CurveConsts<12>& K() { return B200_K(BLS377); }
     static B200_HD const uint32_t* p() { return K().p; }
     static B200_HD const uint32_t* one() { return K().one; }

@@ -44,7 +44,7 @@ struct CurveVTable {
     int scalar_bits;
     size_t aff_size;           // sizeof(G1Affine<N>)
     size_t xyzz_size;          // sizeof(G1XYZZ<N>)
-    int glv;                   // 1: the curve has the GLV endomorphism constants (BLS12 family): one-shot MSMs split the scalars
+    int glv;                   // > 0: bit length of the halves of an exact GLV split (BLS12 family): one-shot MSMs split the scalars
     cudaError_t (*pairing)(int np, size_t n, const uint8_t* g1a, const uint8_t* g2a, const uint8_t* g1b,
                            const uint8_t* g2b, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
     cudaError_t (*fexp)(size_t n, const uint8_t* in, uint8_t* out, uint32_t flags, int* err, cudaStream_t s);
@@ -437,7 +437,7 @@ struct Launch {
         if (b.max_heavy) {
             if ((e = cudaMemsetAsync(b.heavy_n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
             msm_heavy_list_kernel<<<blocks_for(nb, 256), 256, 0, s>>>(nb, b.counts, b.heavy_n, (MsmHeavyItem*)b.heavy_items,
-                                                                      b.max_heavy);
+                                                                      b.max_heavy, (uint32_t)pl.seg);
             B200_COUNT_LAUNCH();
         }
         // buckets in order of decreasing size (equal work per warp), then one thread per bucket
@@ -457,7 +457,7 @@ struct Launch {
                                                               b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
                                                               (Pt*)b.heavy_partial);
             msm_heavy_merge_kernel<C, G><<<hb, 128, 0, s>>>(b.counts, b.heavy_n, (const MsmHeavyItem*)b.heavy_items,
-                                                         (const Pt*)b.heavy_partial, (Pt*)b.buckets);
+                                                         (const Pt*)b.heavy_partial, (Pt*)b.buckets, (uint32_t)pl.seg);
             B200_COUNT_LAUNCH(); B200_COUNT_LAUNCH();
         }
         // (Tried in round 2: accumulating the windows in four groups from the top while side streams reduce each finished
@@ -505,7 +505,7 @@ struct Launch {
     }
     static const CurveVTable* table() {
         static const CurveVTable t = {C::FP_BYTES, C::N, C::SCALAR_BITS, sizeof(G1Affine<C::N>), sizeof(G1XYZZ<C::N>),
-                                      C::FAMILY == FAMILY_BLS12 ? 1 : 0,
+                                      C::GLV_BITS,
                                       &pairing, &fexp, &g1_mul, &g1_mul2, &g1_sum, &g2_mul, &g2_sum, &gt_op, &lines_row_words, &lines_build, &pairing_fixed, &point_codec, &g1_normalize,
                                       (C::N == 12 && C::BETA == -1) ? &hash_to_g1 : nullptr, &msm_points, &msm_tables, &msm, &msm_points_g2, &msm_g2};
         return &t;

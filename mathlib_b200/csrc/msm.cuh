@@ -23,6 +23,7 @@
 
 namespace b200 {
 
+#define B200_MSM_SEG 512          // default segment length of a long bucket run (MsmPlan.seg)
 struct MsmPlan {
     int c;          // window bits
     int W;          // windows
@@ -32,6 +33,7 @@ struct MsmPlan {
     int tables;     // 1: points come from a resident window table, tab[w*stride + i] = 2^start(w) * P_i  (no Horner tail)
     unsigned long long stride;
     int narrow;     // the top `narrow` windows are c-1 bits wide (see msm_plan)
+    int seg;        // a bucket accumulates at most `seg` points on one thread; longer runs are split (msm_heavy_*)
     int glv;        // 1: scalars are split k = k1 + lambda k2 (130-bit halves) over 2n points P_i, phi(P_i) (see msm_plan_glv)
 };
 
@@ -89,19 +91,23 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits, int force_c = 0) {
     p.tables = 0;
     p.stride = 0;
     p.glv = 0;
+    p.seg = B200_MSM_SEG;
     return p;
 }
 
-// GLV plan (BLS12 curves, one-shot MSM of n >= 2^15 points): every scalar is split k = k1 + lambda k2 with k1, k2 < 2^130
-// (g1.cuh glv_split; [lambda](x, y) = (beta x, y) costs one Fp product per point when the points are converted), so the MSM
-// runs over 2n points and 130-bit scalars: half the windows for the same number of bucket additions, and the serial
-// Horner tail is c (W - 1) = 113 doublings instead of 240.  Window sizes that tile 130 bits with at most W narrow windows:
-// c = 17 (2 x 17 + 6 x 16 bits, 8 windows), 15 (9 windows), 14 (10 windows).
-static inline MsmPlan msm_plan_glv(size_t n) {
+// GLV plan (BLS12 curves, one-shot MSM of n >= 2^15 points): every scalar is split exactly, k = k1 + lambda k2 with
+// 0 <= k1 < lambda and k2 <= r / lambda, both below 2^glv_bits (128 on BLS12-381, 127 on BLS12-377; g1.cuh glv_split plus up
+// to three corrections in msm_digits_kernel); [lambda](x, y) = (beta x, y) costs one Fp product per point when the points
+// are converted.  The MSM then runs over 2n points and glv_bits-bit scalars: half the windows for the same number of
+// bucket additions, and the serial Horner tail is 112 doublings instead of 240.  At 2^20 points and up: eight 16-bit
+// windows (c = 17, all narrow: signed digits in windows 0..6, the top window unsigned over 2^16 buckets -- an exact split
+// matters here: with the 130-bit slack of the approximate split the top window's digits would use a sixteenth of its
+// buckets and those would be several times fuller than the rest).
+static inline MsmPlan msm_plan_glv(size_t n, int glv_bits) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= 2 * n) lg++;
     const int c = lg >= 20 ? 17 : (lg >= 17 ? 15 : 14);
-    MsmPlan p = msm_plan(2 * n, 130, c);
+    MsmPlan p = msm_plan(2 * n, glv_bits, c);
     p.glv = 1;
     return p;
 }
@@ -178,6 +184,24 @@ __global__ void msm_digits_kernel(size_t n, const uint8_t* scalars, MsmPlan pl, 
     uint32_t h[9];
     uint32_t k1[5], k2[5];
     G1Ops<C>::glv_split(k1, k2, k);
+    // glv_split under-estimates k2 by at most 3: make the split exact (k1 < lambda) so that both halves fit GLV_BITS
+    {
+        const uint32_t* lam = C::K().glv_lambda;
+        for (int it = 0; it < 3; it++) {
+            uint32_t t[5];
+            t[0] = sub_cc(k1[0], lam[0]);
+            t[1] = subc_cc(k1[1], lam[1]);
+            t[2] = subc_cc(k1[2], lam[2]);
+            t[3] = subc_cc(k1[3], lam[3]);
+            t[4] = subc_cc(k1[4], 0);
+            const uint32_t borrow = subc(0, 0);
+            if (borrow) break;
+            for (int j = 0; j < 5; j++) k1[j] = t[j];
+            k2[0] = add_cc(k2[0], 1);
+            for (int j = 1; j < 4; j++) k2[j] = addc_cc(k2[j], 0);
+            k2[4] = addc(k2[4], 0);
+        }
+    }
     for (int j = 0; j < 9; j++) h[j] = j < 5 ? k1[j] : 0u;
     msm_emit_digits(h, i, 2 * n, pl, digits, counts);
     for (int j = 0; j < 5; j++) h[j] = k2[j];
@@ -272,15 +296,14 @@ static __global__ void msm_size_scatter_kernel(size_t nb, const uint32_t* counts
 // points in msm_accumulate_kernel; every further segment of B200_MSM_SEG points becomes an item (bucket, segment) of a
 // list built on the device, is summed by its own thread, and the partial sums are added to the bucket afterwards.  With
 // uniform scalars the list is empty and the two extra kernels exit at once.
-#define B200_MSM_SEG 512
 struct MsmHeavyItem { uint32_t bucket, seg; };
 static __global__ void msm_heavy_list_kernel(size_t nb, const uint32_t* counts, uint32_t* heavy_n, MsmHeavyItem* items,
-                                             uint32_t max_items) {
+                                             uint32_t max_items, uint32_t seg) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nb) return;
     const uint32_t cnt = counts[t];
-    if (cnt <= B200_MSM_SEG) return;
-    const uint32_t k = (cnt - 1) / B200_MSM_SEG;                       // extra segments 1..k
+    if (cnt <= seg) return;
+    const uint32_t k = (cnt - 1) / seg;                                // extra segments 1..k
     const uint32_t pos = atomicAdd(heavy_n, k);
     for (uint32_t s = 1; s <= k && pos + s - 1 < max_items; s++) items[pos + s - 1] = {(uint32_t)t, s};
 }
@@ -295,8 +318,8 @@ msm_heavy_accumulate_kernel(size_t n, MsmPlan pl, const typename G::Aff* pts, co
     const MsmHeavyItem it = items[id];
     const size_t t = it.bucket, w = t / pl.B;
     if (pl.tables) pts += w * pl.stride;
-    const uint32_t lo = it.seg * B200_MSM_SEG;
-    uint32_t hi = lo + B200_MSM_SEG;
+    const uint32_t lo = it.seg * (uint32_t)pl.seg;
+    uint32_t hi = lo + (uint32_t)pl.seg;
     if (hi > counts[t]) hi = counts[t];
     const uint32_t* run = sorted + w * n + offsets[t];
     typename G::Pt acc;
@@ -313,12 +336,12 @@ msm_heavy_accumulate_kernel(size_t n, MsmPlan pl, const typename G::Aff* pts, co
 template <class C, class G = G1Ops<C>>
 __global__ void __launch_bounds__(128, 2)
 msm_heavy_merge_kernel(const uint32_t* counts, const uint32_t* heavy_n, const MsmHeavyItem* items, const typename G::Pt* partial,
-                       typename G::Pt* buckets) {
+                       typename G::Pt* buckets, uint32_t seg) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= *heavy_n) return;
     const MsmHeavyItem it = items[id];
     if (it.seg != 1) return;
-    const uint32_t k = (counts[it.bucket] - 1) / B200_MSM_SEG;
+    const uint32_t k = (counts[it.bucket] - 1) / seg;
     typename G::Pt acc = buckets[it.bucket];
     for (uint32_t s = 0; s < k; s++) {
         typename G::Pt v = partial[id + s];
@@ -342,7 +365,7 @@ msm_accumulate_kernel(size_t n, MsmPlan pl, const typename G::Aff* pts, const ui
     if (pl.tables) pts += w * pl.stride;
     const uint32_t* run = sorted + w * n + offsets[t];
     uint32_t cnt = counts[t];
-    if (cnt > B200_MSM_SEG) cnt = B200_MSM_SEG;          // the rest of a long run is split over msm_heavy_* threads
+    if (cnt > (uint32_t)pl.seg) cnt = (uint32_t)pl.seg;  // the rest of a long run is split over msm_heavy_* threads
     typename G::Pt acc;
     G::set_inf(acc);
     // software prefetch: the gather of point j+1 (index read + 2*FpBytes random read out of L2/HBM) is issued before

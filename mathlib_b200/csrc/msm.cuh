@@ -95,7 +95,7 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits, int force_c = 0) {
     return p;
 }
 
-// GLV plan (BLS12 curves, one-shot MSM of n >= 2^15 points): every scalar is split exactly, k = k1 + lambda k2 with
+// GLV plan (BLS12 curves, one-shot MSMs): every scalar is split exactly, k = k1 + lambda k2 with
 // 0 <= k1 < lambda and k2 <= r / lambda, both below 2^glv_bits (128 on BLS12-381, 127 on BLS12-377; g1.cuh glv_split plus up
 // to three corrections in msm_digits_kernel); [lambda](x, y) = (beta x, y) costs one Fp product per point when the points
 // are converted.  The MSM then runs over 2n points and glv_bits-bit scalars: half the windows for the same number of
@@ -106,12 +106,14 @@ static inline MsmPlan msm_plan(size_t n, int scalar_bits, int force_c = 0) {
 static inline MsmPlan msm_plan_glv(size_t n, int glv_bits) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= 2 * n) lg++;
-    const int c = lg >= 20 ? 17 : (lg >= 17 ? 15 : 14);
+    const int c = lg >= 20 ? 17 : (lg >= 17 ? 15 : (lg >= 15 ? 14 : 0));      // 0: msm_plan's choice for small inputs
     MsmPlan p = msm_plan(2 * n, glv_bits, c);
     p.glv = 1;
     return p;
 }
-#define B200_MSM_GLV_MIN ((size_t)1 << 15)
+#ifndef B200_MSM_GLV_MIN
+#define B200_MSM_GLV_MIN ((size_t)1)      // every size gains: half the windows means half the serial tail (2^4: 1.96 -> 1.28 ms, 2^13: 2.41 -> 1.79 ms)
+#endif
 
 #if defined(__CUDACC__)
 

@@ -8,9 +8,9 @@ lib.b200_set_stream(torch.cuda.current_stream().cuda_stream)
 cid = int(os.environ.get("CID", "5")); c = m.Curves[cid]
 nmax = 1 << 20
 rng = np.random.default_rng(5)
+import bench
 def rand_scalars(n):
-    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); ks[:, 0] &= 0x0F
-    return torch.from_numpy(ks.reshape(-1)).to(dev)
+    return torch.from_numpy(bench.scalars_mod_r(rng, n, cid).reshape(-1)).to(dev)      # uniform in [0, r)
 d_k = rand_scalars(nmax)
 gen = torch.frombuffer(bytearray(c.GenG1.Bytes()), dtype=torch.uint8).to(dev).repeat(nmax)
 pts = torch.empty(nmax * c.G1ByteSize, dtype=torch.uint8, device=dev)

@@ -109,6 +109,37 @@ def test_msm_golden(m, cid):
         assert out.hex() == case["out"], "n=%d" % n
 
 
+@pytest.mark.parametrize("cid", [4, 5])
+def test_msm_glv_split_edges(m, cid):
+    """One-shot MSMs on the BLS12 curves split every scalar k = k1 + lambda k2 (msm.cuh, GLV plan).  Scalars around the
+    multiples of lambda = x^2 - 1, around r, and the 256-bit maximum, against the oracle's sum of [k_i]P_i."""
+    import random
+    from oracle import codec
+    from oracle.pairing import Pairing
+    from oracle.params import CURVE_IDS as ORACLE_IDS
+    c = m.Curves[cid]
+    P, _ = ORACLE_IDS[cid]
+    C = Pairing(P).C
+    x = {5: 0xd201000000010000, 4: 0x8508c00000000001}[cid]
+    lam = x * x - 1
+    assert (lam * lam + lam + 1) % P.r == 0
+    rnd = random.Random(1200 + cid)
+    ks = [0, 1, lam - 1, lam, lam + 1, 2 * lam - 1, 2 * lam, 3 * lam + 7, (P.r // lam) * lam, (P.r // lam) * lam - 1,
+          P.r - 1, P.r, P.r + 5, (1 << 255) - 19, (1 << 256) - 1, lam * lam % P.r, lam * (lam - 1)]
+    ks += [rnd.randrange(P.r) for _ in range(47)]
+    base = [C.g1_mul(C.g1, rnd.randrange(1, P.r)) for _ in range(8)]
+    pts = [base[i % 8] for i in range(len(ks))]
+    want = None
+    for q, k in zip(pts, ks):
+        want = C.g1_add(want, C.g1_mul(q, k % P.r))
+    got = c.MsmBatch(b"".join(codec.g1_to_bytes(P, q) for q in pts), b"".join(k.to_bytes(32, "big") for k in ks), len(ks))
+    assert got == codec.g1_to_bytes(P, want)
+    # and one term at a time (a single bucket entry per window; k1 = 0 or k2 = 0 leave a half empty)
+    for k in ks[:17]:
+        got = c.MsmBatch(codec.g1_to_bytes(P, base[0]), k.to_bytes(32, "big"), 1)
+        assert got == codec.g1_to_bytes(P, C.g1_mul(base[0], k % P.r)), hex(k)
+
+
 @pytest.mark.parametrize("cid", [1, 4, 5])
 def test_g2_msm_matches_oracle(m, cid):
     """b200_g2_msm against the oracle's sum of [k_i]Q_i: empty, one point, infinity / zero scalar / repeated /

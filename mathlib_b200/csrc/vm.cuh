@@ -322,6 +322,20 @@ struct Vm {
             if (c == 4) shl1(x);
         }
     }
+    // r += mag * x for mag in 0..7 as ONE instruction sequence for every lane (the lanes of a phase carry different
+    // coefficients; a branch per coefficient would serialise them): r += (x & m0) + (2x & m1) + (4x & m2), plain integers
+    static B200_HD void add_small_multiple_uniform(E1& r, const E1& x, uint32_t mag) {
+        E1 v = x;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const uint32_t mask = 0u - ((mag >> b) & 1u);
+            r.l[0] = add_cc(r.l[0], v.l[0] & mask);
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], v.l[i] & mask);
+            r.l[N - 1] = addc(r.l[N - 1], v.l[N - 1] & mask);
+            if (b < 2) shl1(v);
+        }
+    }
     // v[N..2N) += x: adds x R to the value under reduction, i.e. x to the reduced result
     static B200_HD void wide_add_high(uint32_t* v, const E1& x) {
         v[N] = add_cc(v[N], x.l[0]);
@@ -459,7 +473,44 @@ struct Vm {
             }
             if (!folded && scale != 1) { mul_small(res.c0, res.c0, scale); mul_small(res.c1, res.c1, scale); }
         } else {
-            T::f2_zero(res);
+            // LIN: sum c_i mod(x_i) as plain integers -- a negative coefficient becomes |c| (p - x), small multiples are shifts
+            // and masked additions, ONE instruction sequence whatever the coefficients (the six lanes of a linear phase carry
+            // different ones: with a modular doubling / addition / subtraction per coefficient the warp ran every variant in
+            // turn, ~2,000 instructions per phase) -- then `levels` conditional subtractions (4p, 2p, p): the compiler's
+            // bound  sum |c_i| bound(x_i) <= 2^levels  (compiler.lin_levels).
+            E1 r0, r1;
+            F::zero(r0);
+            F::zero(r1);
+            for (uint32_t t = 0; t < nl; t++) {
+                const uint32_t lw = w[8 + t];
+                const uint32_t* px = slot_ptr(slots, kb_off, bases, lw & 0x7FF);
+                int coef = (int)((lw >> 11) & 31);
+                if (coef >= 16) coef -= 32;
+                uint32_t m = (lw >> 16) & 15;
+                if (coef < 0) m ^= VM_NEG;
+                const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+                E1 x0, x1;
+                if (C::LAZY_MODS) {
+                    load1(x0, px);
+                    load1(x1, px + N);
+                    if (m) lazy_mods(x0, x1, m);
+                } else {
+                    E2 x;
+                    load2(x, px);
+                    if (m & ~VM_NEG) apply_mod(x, m & ~VM_NEG);
+                    x0 = x.c0; x1 = x.c1;
+                    if (m & VM_NEG) { p_minus_c(x0); p_minus_c(x1); }
+                }
+                add_small_multiple_uniform(r0, x0, mag);
+                add_small_multiple_uniform(r1, x1, mag);
+            }
+            const uint32_t levels = (hdr >> 18) & 3;
+            if (levels >= 3) { cond_sub_kp(r0, 2); cond_sub_kp(r1, 2); }
+            if (levels >= 2) { cond_sub_kp(r0, 1); cond_sub_kp(r1, 1); }
+            cond_sub_kp(r0, 0);
+            cond_sub_kp(r1, 0);
+            res.c0 = r0; res.c1 = r1;
+            folded = true;                          // the linear terms are consumed
         }
         if (!folded) {
             for (uint32_t t = 0; t < nl; t++) {
@@ -614,7 +665,35 @@ struct Vm {
             redc(r, V, levels);
             if (!folded && scale != 1) mul_small(r, r, scale);
         } else {
+            // LIN as a plain integer sum with one instruction sequence for every coefficient, as in exec_op
             F::zero(r);
+            for (uint32_t t = 0; t < nl; t++) {
+                const uint32_t lw = w[8 + t];
+                const uint32_t* px = slot_ptr(slots, kb_off, bases, lw & 0x7FF);
+                int coef = (int)((lw >> 11) & 31);
+                if (coef >= 16) coef -= 32;
+                uint32_t m = (lw >> 16) & 15;
+                if (coef < 0) m ^= VM_NEG;
+                const uint32_t mag = (uint32_t)(coef < 0 ? -coef : coef);
+                E1 x0, x1;
+                if (C::LAZY_MODS) {
+                    load1(x0, px);
+                    load1(x1, px + N);
+                    if (m) lazy_mods(x0, x1, m);
+                } else {
+                    E2 x;
+                    load2(x, px);
+                    if (m & ~VM_NEG) apply_mod(x, m & ~VM_NEG);
+                    x0 = x.c0; x1 = x.c1;
+                    if (m & VM_NEG) { p_minus_c(x0); p_minus_c(x1); }
+                }
+                add_small_multiple_uniform(r, sub == 0 ? x0 : x1, mag);
+            }
+            const uint32_t levels = (hdr >> 18) & 3;
+            if (levels >= 3) cond_sub_kp(r, 2);
+            if (levels >= 2) cond_sub_kp(r, 1);
+            cond_sub_kp(r, 0);
+            folded = true;
         }
         if (!folded) {
             for (uint32_t t = 0; t < nl; t++) {

@@ -89,6 +89,22 @@ def dot_bounds(terms):
     raise AssertionError("dot product too wide for the field's head room: k = %d" % k)
 
 
+def lin_levels(v):
+    """`levels` of a LIN op evaluated as a plain integer sum (csrc/vm.cuh exec_op): the value stays below
+    sum |c_i| bound(mod(x_i)) p, which must fit N words and be at most 2^levels p (levels <= 3; the interpreter subtracts
+    4p, 2p, p conditionally)."""
+    p, R = _field['p'], 1 << (32 * _field['limbs'])
+    tot = 0
+    for (_, c, m) in v.lin:
+        assert abs(c) <= 7, "LIN coefficient beyond the 3-bit small multiple"
+        tot += abs(c) * max(operand_bounds(m))
+    assert tot * p < R, "LIN sum overflows N words: %d p" % tot
+    for levels in (1, 2, 3):
+        if tot <= (1 << levels) and (1 << (levels - 1)) * p < R:
+            return levels
+    raise AssertionError("LIN sum too wide: %d p" % tot)
+
+
 FOLD_SCALES = (1, 2, 3, 4, 6)
 
 
@@ -355,7 +371,8 @@ def compile_program(name, outputs, temp_slots, pinned_reads=()):
         # so lanes with fewer terms do not serialise against the others
         pmax = max([len(v.terms) for v in vs if v.kind == 'dot'] + [0])
         fold = {id(v): fold_bounds(v) for v in vs if v.kind == 'dot'}
-        levels = max([fold[id(v)] or dot_bounds(v.terms)[1] for v in vs if v.kind == 'dot'] + [1])
+        levels = max([fold[id(v)] or dot_bounds(v.terms)[1] for v in vs if v.kind == 'dot'] +
+                     [lin_levels(v) for v in vs if v.kind == 'lin'] + [1])
         for v in lanes:
             w = [0] * OP_WORDS
             if v is not None:

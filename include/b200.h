@@ -113,7 +113,9 @@ int b200_g1_mul2_batch(int curve, size_t n, const void* P, const void* e_be32, c
                        void* out, uint32_t flags);
 
 /* driver.Curve.MultiScalarMul (reference driver/math.go:170): out = sum_i [scalars[i]] pts[i], one affine G1.
-   n == 0 gives infinity. */
+   n == 0 gives infinity.  Scalars are any 256-bit values (reduced mod r on the device).  The points must lie in the
+   prime-order subgroup -- what mathlib's deserialisers guarantee and gnark's MultiExp assumes as well: on the BLS12 curves
+   the scalars are split with the GLV endomorphism (k = k1 + lambda k2, [lambda](x, y) = (beta x, y)). */
 int b200_g1_msm(int curve, size_t n, const void* pts, const void* scalars_be32, void* out, uint32_t flags);
 
 /* Resident base points: upload once, run many MSMs against them (scalars only cross PCIe). */

@@ -345,6 +345,10 @@ struct FpOps {
     static B200_HD_NOINLINE E mulv(E a, E b) { E r; mul(r, a, b); return r; }
     static B200_HD void mulx(E& r, const E& a, const E& b) { r = mulv(a, b); }
     static B200_HD void sqrx(E& r, const E& a) { r = mulv(a, a); }
+    // a0 b0 + a1 b1 with ONE Montgomery reduction (mul_dot<2>: 3N^2 + N multiply-accumulates instead of 4N^2 + 2N), out of
+    // line and by value like mulv
+    static B200_HD_NOINLINE E mulv2(E a0, E b0, E a1, E b1) { E r; mul_dot2(r, a0, b0, a1, b1); return r; }
+    static B200_HD void mulx2(E& r, const E& a0, const E& b0, const E& a1, const E& b1) { r = mulv2(a0, b0, a1, b1); }
 
     // Montgomery form conversions
     static B200_HD void to_mont(E& r, const E& a) {

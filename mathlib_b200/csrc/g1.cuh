@@ -55,9 +55,8 @@ struct G1Ops {
         F::sqrx(p.x, M);
         F::sub(p.x, p.x, S); F::sub(p.x, p.x, S);
         F::sub(t, S, p.x);
-        F::mulx(t, M, t);
-        F::mulx(U, W, a.y);
-        F::sub(p.y, t, U);
+        F::neg(U, a.y);
+        F::mulx2(p.y, M, t, W, U);     // M (S - X3) - W Y1: two products, one reduction
         p.zz = V;
         p.zzz = W;
     }
@@ -71,12 +70,11 @@ struct G1Ops {
         F::mulx(S, p.x, V);
         F::sqrx(M, p.x);
         F::dbl(t, M); F::add(M, M, t);
-        F::mulx(U, W, p.y);            // W*Y1
+        F::neg(U, p.y);
         F::sqrx(p.x, M);
         F::sub(p.x, p.x, S); F::sub(p.x, p.x, S);
         F::sub(t, S, p.x);
-        F::mulx(t, M, t);
-        F::sub(p.y, t, U);
+        F::mulx2(p.y, M, t, W, U);     // M (S - X3) - W Y1: two products, one reduction
         F::mulx(p.zz, V, p.zz);
         F::mulx(p.zzz, W, p.zzz);
     }
@@ -99,9 +97,9 @@ struct G1Ops {
         F::sqrx(t, R);
         F::sub(t, t, PPP); F::sub(t, t, Q); F::sub(t, t, Q);   // X3
         F::sub(Q, Q, t);
-        F::mulx(Q, R, Q);
-        F::mulx(S2, p.y, PPP);
-        F::sub(p.y, Q, S2);
+        // Y3 = R (Q - X3) - Y PPP = R (Q - X3) + (p - Y) PPP: two products, one reduction
+        F::neg(S2, p.y);
+        F::mulx2(p.y, R, Q, S2, PPP);
         p.x = t;
         F::mulx(p.zz, p.zz, PP);
         F::mulx(p.zzz, p.zzz, PPP);
@@ -127,9 +125,8 @@ struct G1Ops {
         F::sqrx(t, R);
         F::sub(t, t, PPP); F::sub(t, t, Q); F::sub(t, t, Q);   // X3
         F::sub(Q, Q, t);
-        F::mulx(Q, R, Q);
-        F::mulx(S1, S1, PPP);
-        F::sub(p.y, Q, S1);
+        F::neg(S1, S1);
+        F::mulx2(p.y, R, Q, S1, PPP);  // R (Q - X3) - S1 PPP: two products, one reduction
         p.x = t;
         F::mulx(p.zz, p.zz, q.zz);
         F::mulx(p.zz, p.zz, PP);

@@ -49,19 +49,21 @@ struct Tower {
         }
     }
 
-    static B200_HD_NOINLINE void f2_mul(E2& r, const E2& a, const E2& b) {
-        E1 t0, t1, t2, s0, s1;
-        F::add(s0, a.c0, a.c1);
-        F::add(s1, b.c0, b.c1);
-        F::mul(t0, a.c0, b.c0);
-        F::mul(t1, a.c1, b.c1);
-        F::mul(t2, s0, s1);
-        F::sub(t2, t2, t0);
-        F::sub(r.c1, t2, t1);
-        fp_mul_beta(t1, t1);
-        F::add(r.c0, t0, t1);
+    // Fp2 product and square, out of line with operands and result BY VALUE (48 words in, 24 out in registers: references
+    // would push every operand through a local-memory stack slot, as the round-1 G1 code did).  The product is two
+    // two-operand Montgomery products (FpOps::mul_dot<2>: one reduction per component, 6N^2 + 2N multiply-accumulates and
+    // no Karatsuba additions) instead of three full ones:  c1 = a0 b1 + a1 b0,  c0 = a0 b0 + (BETA a1) b1.
+    static B200_HD_NOINLINE E2 f2_mulv(E2 a, E2 b) {
+        E2 r;
+        E1 n1;
+        F::mul_dot2(r.c1, a.c0, b.c1, a.c1, b.c0);
+        fp_mul_beta(n1, a.c1);
+        F::mul_dot2(r.c0, a.c0, b.c0, n1, b.c1);
+        return r;
     }
-    static B200_HD_NOINLINE void f2_sqr(E2& r, const E2& a) {
+    static B200_HD void f2_mul(E2& r, const E2& a, const E2& b) { r = f2_mulv(a, b); }
+    static B200_HD_NOINLINE E2 f2_sqrv(E2 a) {
+        E2 r;
         E1 s, d, v;
         F::mul(v, a.c0, a.c1);
         F::add(s, a.c0, a.c1);
@@ -77,7 +79,9 @@ struct Tower {
             F::add(r.c0, t, d);
         }
         F::dbl(r.c1, v);
+        return r;
     }
+    static B200_HD void f2_sqr(E2& r, const E2& a) { r = f2_sqrv(a); }
     // r = a * s, s in Fp
     static B200_HD void f2_mul_fp(E2& r, const E2& a, const E1& s) {
         F::mul(r.c0, a.c0, s);

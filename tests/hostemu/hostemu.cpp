@@ -16,6 +16,7 @@ template <class C> static void t_mul(const uint32_t* a, const uint32_t* b, uint3
         case 8: F::inv_fermat(z, x); break;
         case 6: F::to_mont(z, x); break;
         case 7: F::from_mont(z, x); break;
+        case 9: F::sqr(z, x); break;
     }
     for (int i = 0; i < C::N; i++) o[i] = z.l[i];
 }

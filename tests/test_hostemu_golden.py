@@ -142,6 +142,24 @@ def test_fp_inverse_and_dot(hostemu):
                 assert val(o) == sum(a[t] * b[t] for t in range(T)) * pow(R, -1, P.p) % P.p
 
 
+def test_fp_dedicated_squaring(hostemu):
+    """FpOps::sqr (upper-triangle wide square + word-sliding reduction) == a * a / R mod p, incl. 0, 1, p - 1 and values with
+    all-ones limbs (every carry deposit of the wide square is exercised)."""
+    import random
+    from oracle.params import BN254, BLS12_381, BLS12_377
+    rnd = random.Random(23)
+    for ci, P in enumerate([BN254, BLS12_381, BLS12_377]):
+        n = P.limbs32
+        R = 1 << (32 * n)
+        arr = lambda v: (ctypes.c_uint32 * n)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+        val = lambda o: sum(int(x) << (32 * i) for i, x in enumerate(o))
+        ones = [((1 << (32 * k)) - 1) % P.p for k in range(1, n + 1)] + [(P.p - 1) ^ ((1 << (32 * k)) - 1) for k in range(1, n)]
+        for a in [0, 1, 2, P.p - 1, P.p - 2, R % P.p] + [v % P.p for v in ones] + [rnd.randrange(P.p) for _ in range(200)]:
+            o = (ctypes.c_uint32 * n)()
+            hostemu.he_fp_op(ci, 9, arr(a), arr(0), o)
+            assert val(o) == a * a * pow(R, -1, P.p) % P.p, hex(a)
+
+
 @pytest.mark.parametrize("cid", [1, 4, 5])
 def test_vm_fixed_q_and_gt_exp_on_host(hostemu, cid):
     """The C++ control flow of the fixed-Q kernels (precompute_lines + miller_fixed) and of the Gt.Exp ladder, host-emulated:
